@@ -358,23 +358,27 @@ def synth_layer_inputs(spec: LayerSpec, batch: int, hw: Optional[Tuple[int, int]
                        seq: Optional[int], gen: torch.Generator,
                        dtype=torch.float32) -> LayerInputs:
     """a ~ N(0,1) with the layer's input shape, g ~ N(0,1)/batch with its
-    output shape (BASELINE.md section 2 'injection mode')."""
+    output shape (BASELINE.md section 2 'injection mode').  Values are always
+    DRAWN in float32 (so the fp32 and fp64 runs see the same numbers) and then
+    cast to ``dtype``."""
+    f32 = torch.float32
     if spec.kind == 'conv2d':
         h, w = hw
         oh, ow = conv_out_hw(spec, h, w)
-        a = torch.randn(batch, spec.in_channels, h, w, generator=gen, dtype=dtype)
-        g = torch.randn(batch, spec.out_features, oh, ow, generator=gen, dtype=dtype) / batch
+        a = torch.randn(batch, spec.in_channels, h, w, generator=gen, dtype=f32)
+        g = torch.randn(batch, spec.out_features, oh, ow, generator=gen, dtype=f32) / batch
     else:
         if seq is None:
-            a = torch.randn(batch, spec.in_features, generator=gen, dtype=dtype)
-            g = torch.randn(batch, spec.out_features, generator=gen, dtype=dtype) / batch
+            a = torch.randn(batch, spec.in_features, generator=gen, dtype=f32)
+            g = torch.randn(batch, spec.out_features, generator=gen, dtype=f32) / batch
         else:
-            a = torch.randn(batch, seq, spec.in_features, generator=gen, dtype=dtype)
-            g = torch.randn(batch, seq, spec.out_features, generator=gen, dtype=dtype) / batch
-    return LayerInputs(a, g)
+            a = torch.randn(batch, seq, spec.in_features, generator=gen, dtype=f32)
+            g = torch.randn(batch, seq, spec.out_features, generator=gen, dtype=f32) / batch
+    return LayerInputs(a.to(dtype), g.to(dtype))
 
 
 def synth_grads(spec: LayerSpec, gen: torch.Generator, dtype=torch.float32):
-    w = torch.randn(*spec.weight_shape(), generator=gen, dtype=dtype)
-    b = torch.randn(spec.out_features, generator=gen, dtype=dtype) if spec.has_bias else None
+    w = torch.randn(*spec.weight_shape(), generator=gen, dtype=torch.float32).to(dtype)
+    b = (torch.randn(spec.out_features, generator=gen, dtype=torch.float32).to(dtype)
+         if spec.has_bias else None)
     return w, b

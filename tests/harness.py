@@ -78,3 +78,23 @@ def rel_err(x, ref):
     x = np.asarray(x, dtype=np.float64); ref = np.asarray(ref, dtype=np.float64)
     den = np.linalg.norm(ref)
     return float(np.linalg.norm(x - ref) / den) if den > 0 else float(np.linalg.norm(x))
+
+
+def noise_by_kind(fx):
+    """Worst fp32-vs-fp64 distance of the REFERENCE ITSELF per quantity kind
+    (wgrad, bgrad, precon, A, G, dA, dG, invA, invG) over all layers, steps and
+    ranks of a fixture: the noise floor any fp32 implementation of this path
+    lives on (DESIGN.md 'parity definition')."""
+    worst = {}
+    for k in fx:
+        if k.startswith('ref32_'):
+            kind = k.rsplit('_', 1)[-1]
+            worst[kind] = max(worst.get(kind, 0.0), rel_err(fx[k], fx['ref64_' + k[6:]]))
+    return worst
+
+
+def tolerance(kind, noise, floor=2e-5, mult=3.0):
+    """Parity bar for an fp32 result against the fp64 truth: north_star's 1e-4
+    relative, widened only where the reference's own fp32 run is already
+    further than 1e-4/3 from the truth (then 3x that noise)."""
+    return max(mult * noise.get(kind, 0.0), floor)
