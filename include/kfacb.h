@@ -1,0 +1,195 @@
+/*
+ * kfacb.h -- C ABI of libkfacb.so, the sm_100a CUDA implementation of the
+ * DP-KFAC `preconditioner.step()` hot path.
+ *
+ * The reference (lzhangbv/kfac_pytorch @ c45acb8) has NO FFI on this path: its
+ * boundary is the Python API of package `kfac`.  This
+ * library is what a native replacement of the reference's per-layer math
+ * exposes; every entry point cites the reference code it replaces (paths
+ * relative to the reference repo root).  The Python package
+ * `kfac_pytorch_b200` (and the `kfac` drop-in shim) binds it with ctypes; the
+ * binding a reference maintainer would add is shown in INTEGRATION.md.
+ *
+ * Conventions
+ *  - plain C: raw device pointers, sizes, a CUDA stream handle; no torch types.
+ *  - every function returns a kfacb_status (0 = ok).  No C++ exceptions cross
+ *    the boundary, nothing aborts.  kfacb_last_error() gives a message for the
+ *    calling thread's last non-zero status.
+ *  - the library never allocates or frees device memory: the caller owns all
+ *    buffers, including workspaces whose sizes come from the *_workspace_bytes
+ *    queries.  Workspaces must be 256-byte aligned.
+ *  - all work is enqueued on `stream`; no call synchronises the device.
+ *  - host arrays (descriptors, pointer tables) are read before the call
+ *    returns and may be reused immediately.
+ *  - all matrices are dense row-major fp32.
+ *  - a NULL entry in a per-layer pointer table means "this rank does not own
+ *    that layer/factor": the layer is skipped (reference: the
+ *    `backend.comm.rank() == rank_a` guards, kfac_preconditioner_inv_dp.py:79,86).
+ */
+#ifndef KFACB_H_
+#define KFACB_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* kfacb_stream_t;              /* cudaStream_t */
+
+typedef enum {
+    KFACB_OK = 0,
+    KFACB_ERR_ARG = 1,          /* bad shape / null pointer / unsupported layer kind
+                                   (reference: NotImplementedError, kfac/utils.py:82,115) */
+    KFACB_ERR_CUDA = 2,         /* a CUDA runtime call failed */
+    KFACB_ERR_WORKSPACE = 3,    /* workspace too small or misaligned */
+    KFACB_ERR_ARCH = 4          /* device is not sm_100 */
+} kfacb_status;
+
+/* kinds of preconditioned layers (reference: class-name match on
+ * {'Linear','Conv2d'}, kfac/kfac_preconditioner_base.py:132-147) */
+enum { KFACB_LINEAR = 0, KFACB_CONV2D = 1 };
+
+/* Shape of one layer.  Built once at hook-registration time from the module
+ * (what the reference reads off `layer` in kfac/utils.py:85-103,118-140). */
+typedef struct {
+    int32_t kind;       /* KFACB_LINEAR | KFACB_CONV2D */
+    int32_t has_bias;   /* appends the homogeneous "ones" column to A and the bias column to the gradient */
+    int32_t batch;      /* B: leading dimension of a and g */
+    int32_t seq;        /* linear: T when a/g are (B,T,D) -- they are mean-reduced over T
+                           (kfac/utils.py:98-99,133-134); 1 for (B,D) inputs; conv: 1 */
+    int32_t in_c;       /* linear: in_features; conv: C_in */
+    int32_t out_c;      /* linear: out_features; conv: C_out */
+    int32_t in_h, in_w; /* conv input spatial size (unused for linear) */
+    int32_t kh, kw;     /* conv kernel */
+    int32_t sh, sw;     /* conv stride */
+    int32_t ph, pw;     /* conv zero padding (dilation/groups are ignored, as in kfac/utils.py:33-54) */
+    int32_t out_h, out_w;
+} kfacb_layer_t;
+
+/* dA = in_c*kh*kw (+1 if bias)  [linear: kh = kw = 1];  dG = out_c */
+int32_t kfacb_layer_dA(const kfacb_layer_t* l);
+int32_t kfacb_layer_dG(const kfacb_layer_t* l);
+
+int         kfacb_version(void);
+const char* kfacb_last_error(void);
+/* fills SM count and compute capability of the current device */
+int         kfacb_device_info(int32_t* sm_count, int32_t* cc_major, int32_t* cc_minor);
+
+/* ---------------------------------------------------------------------------
+ * (1) Kronecker-factor accumulation fused with the running average.
+ * Replaces ComputeA / ComputeG / update_running_avg and the identity
+ * initialisation: kfac/utils.py:33-54,66-140 and
+ * kfac/kfac_preconditioner_inv_dp.py:75-90.
+ *
+ *   A_new = [P 1]^T [P 1] / (B*S^2)  (conv; P = im2col rows, never materialised)
+ *         =  [a 1]^T [a 1] / B       (linear; a mean-reduced over T first)
+ *   G_new = B*S * g_rows^T g_rows    (conv)      = B * g^T g   (linear)
+ *   first_step:  factor <- (1-alpha)*I + alpha*new     (identity init, inv_dp.py:82-84)
+ *   otherwise :  factor <- (1-alpha)*factor + alpha*new   (alpha = factor_decay)
+ *
+ * a[i]: layer input  (B,C,H,W) | (B,D) | (B,T,D);  g[i]: grad wrt the layer
+ * output (B,C_out,oh,ow) | (B,D') | (B,T,D'), of the batch-AVERAGED loss.
+ * A[i] is dA x dA, G[i] is dG x dG.  a[i]==NULL skips A, g[i]==NULL skips G.
+ * ------------------------------------------------------------------------- */
+size_t kfacb_factor_workspace_bytes(const kfacb_layer_t* layers, int32_t count);
+int    kfacb_factor_update(const kfacb_layer_t* layers, int32_t count,
+                           const float* const* a, const float* const* g,
+                           float* const* A, float* const* G,
+                           float alpha, int32_t first_step,
+                           void* workspace, size_t workspace_bytes,
+                           kfacb_stream_t stream);
+
+/* ---------------------------------------------------------------------------
+ * (2a) Batched symmetric eigendecomposition with eigenvalue floor.
+ * Replaces mat_eig + the floor mask: kfac/utils.py:22-25 and
+ * kfac/kfac_preconditioner_eigen_dp.py:62-75 (and the unused cuSOLVER wrapper
+ * packages/tcmm/src/tcmm_kernel.cu:56-116).
+ *
+ * For each i: M[i] (n[i] x n[i], symmetric, read only) = Q diag(d) Q^T with d
+ * ascending, eigenvectors in the COLUMNS of Q[i] (row-major n x n), then
+ * d <- d * (d > eps_floor).  Jacobi based (one CTA per matrix in shared memory
+ * for n <= 128, blocked one-sided Jacobi above); eigenvectors are defined up
+ * to sign / rotation inside degenerate clusters.
+ * sweeps_out (device int32[count], may be NULL) receives the number of sweeps.
+ * ------------------------------------------------------------------------- */
+size_t kfacb_eigh_workspace_bytes(const int32_t* n, int32_t count);
+int    kfacb_eigh_batched(const int32_t* n, int32_t count,
+                          const float* const* M, float* const* Q, float* const* d,
+                          float eps_floor, int32_t* sweeps_out,
+                          void* workspace, size_t workspace_bytes,
+                          kfacb_stream_t stream);
+
+/* ---------------------------------------------------------------------------
+ * (2b) pi-damped SPD inverse.  Replaces
+ * kfac/kfac_preconditioner_inv_dp.py:98-123, _add_value_to_diagonal
+ * (kfac_preconditioner_inv.py:106-107) and mat_inv (kfac/utils.py:11-16).
+ *
+ *   pi = sqrt((tr A / dA) / (tr G / dG))
+ *   A += sqrt(damping)*pi * I   IN PLACE (persists in the running factor)
+ *   G += sqrt(damping)/pi * I   IN PLACE
+ *   invA = A^-1, invG = G^-1    (full symmetric inverses)
+ * A[i]==NULL skips layer i.
+ * ------------------------------------------------------------------------- */
+size_t kfacb_spd_inverse_workspace_bytes(const int32_t* nA, const int32_t* nG, int32_t count);
+int    kfacb_pi_damped_inverse(const int32_t* nA, const int32_t* nG, int32_t count,
+                               float* const* A, float* const* G,
+                               float* const* invA, float* const* invG,
+                               float damping,
+                               void* workspace, size_t workspace_bytes,
+                               kfacb_stream_t stream);
+
+/* ---------------------------------------------------------------------------
+ * (3) Two-sided preconditioned gradient.  The gradient matrix
+ * [W.view(out,-1) | b] (kfac_preconditioner_inv.py:145-154) is read straight
+ * from wgrad/bgrad (no concatenated copy).
+ *
+ * eigen   (kfac_preconditioner_eigen_dp.py:87-89):
+ *     V1 = QG^T grad QA;  V2 = V1 / (dG dA^T + damping);  out = QG V2 QA^T
+ * inverse (kfac_preconditioner_inv_dp.py:135):
+ *     out = invG grad invA
+ * out[i] is the dG x dA preconditioned gradient (`m_precon_grad`), the buffer
+ * that is exchanged between ranks.  wgrad[i]==NULL skips layer i.
+ * ------------------------------------------------------------------------- */
+size_t kfacb_precond_workspace_bytes(const kfacb_layer_t* layers, int32_t count);
+int    kfacb_precond_eigen(const kfacb_layer_t* layers, int32_t count,
+                           const float* const* QA, const float* const* QG,
+                           const float* const* dA, const float* const* dG,
+                           const float* const* wgrad, const float* const* bgrad,
+                           float* const* out, float damping,
+                           void* workspace, size_t workspace_bytes,
+                           kfacb_stream_t stream);
+int    kfacb_precond_inverse(const kfacb_layer_t* layers, int32_t count,
+                             const float* const* invA, const float* const* invG,
+                             const float* const* wgrad, const float* const* bgrad,
+                             float* const* out,
+                             void* workspace, size_t workspace_bytes,
+                             kfacb_stream_t stream);
+
+/* ---------------------------------------------------------------------------
+ * (4) KL-clip and in-place gradient rewrite.  Replaces
+ * _reshape_preconditioned_grad + _update_grad_in_place,
+ * kfac_preconditioner_inv.py:178-217, without the per-tensor `.item()` syncs:
+ *
+ *   vg_sum = sum_layers sum(v * grad) * lr^2        (grad = the pre-overwrite grads)
+ *   nu     = kl_clip > 0 ? min(1, sqrt(kl_clip / |vg_sum|)) : 1     (force_nu_one -> 1)
+ *   wgrad  <- nu * v[:, :-1],  bgrad <- nu * v[:, -1]
+ *
+ * precon[i] must be non-NULL for EVERY layer (after the exchange all ranks hold
+ * all preconditioned gradients).  nu_out: device float[1] receiving nu.
+ * workspace: kfacb_finalize_workspace_bytes(count) bytes.
+ * ------------------------------------------------------------------------- */
+size_t kfacb_finalize_workspace_bytes(const kfacb_layer_t* layers, int32_t count);
+int    kfacb_finalize_grads(const kfacb_layer_t* layers, int32_t count,
+                            const float* const* precon,
+                            float* const* wgrad, float* const* bgrad,
+                            float lr, float kl_clip, int32_t force_nu_one,
+                            float* nu_out,
+                            void* workspace, size_t workspace_bytes,
+                            kfacb_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KFACB_H_ */

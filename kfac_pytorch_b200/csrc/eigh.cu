@@ -1,0 +1,695 @@
+// eigh.cu -- batched symmetric eigendecomposition (C-ABI: kfacb_eigh_batched).
+// Replaces torch.linalg.eigh + the eigenvalue floor of the reference
+// (kfac/utils.py:22-25, kfac/kfac_preconditioner_eigen_dp.py:62-75).
+//
+// Two paths, both Jacobi (high relative accuracy, embarrassingly parallel,
+// no library dependency):
+//   n <= 128 : one CTA per matrix, two-sided cyclic Jacobi with the round-robin
+//              parallel ordering, matrix and eigenvector accumulator resident
+//              in shared memory.
+//   n  > 128 : blocked ONE-SIDED (Hestenes) Jacobi.  The work array
+//              X = [W^T | V^T] (n_pad x 2 n_pad, row i = column i of W = A V and
+//              of V) starts as [A | I].  A round pairs up 32-row blocks with the
+//              round-robin schedule; per pair: 64x64 Gram of the W rows
+//              (split-K), two-sided Jacobi of the Gram in shared memory -> U,
+//              rows <- U^T rows (W and V together).  All pairs of all matrices
+//              of the batch run in the same launches.  At convergence the W
+//              rows are mutually orthogonal: W = V diag(lambda).  Eigenvalues
+//              are then recomputed as Rayleigh quotients v^T A v (second-order
+//              accurate), sorted ascending, floored, and V is written out
+//              column-wise.
+#include "common.cuh"
+
+namespace kfacb {
+
+constexpr int BJ_B = 32;              // rows per block
+constexpr int BJ_M = 2 * BJ_B;        // rows per pair = size of the inner eigenproblem
+constexpr int BJ_KCHUNK = 256;        // Gram split-K chunk
+constexpr int BJ_MAX_SWEEPS = 16;
+constexpr int DIRECT_MAX_N = 128;
+
+struct BjMat {
+    float* X;             // n_pad x 2 n_pad work array
+    const float* A;       // input matrix n x n
+    float* Q;             // output eigenvectors (columns) n x n
+    float* d;             // output eigenvalues n
+    float* lam;           // workspace n_pad (rayleigh quotients)
+    float* nrm;           // workspace n_pad (||v_i||^2)
+    int* perm;            // workspace n
+    int n, n_pad, p;      // p = even number of blocks (incl. a dummy when odd)
+    int nblk;             // real number of blocks
+    int pair_begin;       // first global pair index of this matrix
+    int ksplit;           // Gram split-K factor
+    float tol_conv;       // relative off-diagonal size that still counts as "not converged"
+};
+
+struct BjState {          // per matrix, device
+    int converged;
+    int rot;              // significant rotations in the current sweep
+    int sweeps;
+};
+
+// ---------------------------------------------------------------------------
+// two-sided cyclic Jacobi on an m x m symmetric matrix in shared memory
+// (m even, pitch P odd).  On exit S is diagonal (to tolerance) and U holds the
+// accumulated rotations (columns = eigenvectors of the input).  Returns the
+// number of sweeps executed; *sig_out = 1 if any rotation exceeded sig_tol.
+// All threads of the CTA must call it.
+// ---------------------------------------------------------------------------
+__device__ int jacobi_smem(float* S, float* U, int m, int P, float tol_rel, float abs_thr,
+                           float sig_tol, int max_sweeps, int* sig_out) {
+    __shared__ float s_c[DIRECT_MAX_N / 2], s_s[DIRECT_MAX_N / 2];
+    __shared__ int s_p[DIRECT_MAX_N / 2], s_q[DIRECT_MAX_N / 2];
+    __shared__ int s_flag, s_sig;
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const int half = m >> 1, mm1 = m - 1;
+    if (tid == 0) s_sig = 0;
+    int sweeps = 0;
+    int prev_p = -1, prev_q = -1;
+    for (int sw = 0; sw < max_sweeps; ++sw) {
+        __syncthreads();
+        if (tid == 0) s_flag = 0;
+        __syncthreads();
+        for (int r = 0; r < mm1; ++r) {
+            if (tid < half) {
+                if (prev_p >= 0) { S[prev_p * P + prev_q] = 0.f; S[prev_q * P + prev_p] = 0.f; prev_p = -1; }
+                int p, q;
+                if (tid == 0) { p = mm1; q = r; }
+                else { p = (r + tid) % mm1; q = (r - tid + mm1) % mm1; }
+                if (p > q) { const int t = p; p = q; q = t; }
+                const float app = S[p * P + p], aqq = S[q * P + q], apq = S[p * P + q];
+                float c = 1.f, s = 0.f;
+                const float mag = fabsf(apq);
+                const float ref = sqrtf(fabsf(app) * fabsf(aqq));
+                if (mag > tol_rel * ref && mag > abs_thr) {
+                    const float tau = (aqq - app) / (2.f * apq);
+                    const float t = (tau >= 0.f ? 1.f : -1.f) / (fabsf(tau) + sqrtf(1.f + tau * tau));
+                    c = rsqrtf(1.f + t * t);
+                    s = t * c;
+                    s_flag = 1;
+                    if (mag > sig_tol * ref) s_sig = 1;
+                    prev_p = p; prev_q = q;
+                }
+                s_c[tid] = c; s_s[tid] = s; s_p[tid] = p; s_q[tid] = q;
+            }
+            __syncthreads();
+            // column rotations: S <- S J, U <- U J
+            for (int e = tid; e < half * m; e += nt) {
+                const int k = e / m, i = e - k * m;
+                const float s = s_s[k];
+                if (s != 0.f) {
+                    const float c = s_c[k];
+                    const int p = s_p[k], q = s_q[k];
+                    float x = S[i * P + p], y = S[i * P + q];
+                    S[i * P + p] = c * x - s * y;
+                    S[i * P + q] = s * x + c * y;
+                    x = U[i * P + p]; y = U[i * P + q];
+                    U[i * P + p] = c * x - s * y;
+                    U[i * P + q] = s * x + c * y;
+                }
+            }
+            __syncthreads();
+            // row rotations: S <- J^T S
+            for (int e = tid; e < half * m; e += nt) {
+                const int k = e / m, j = e - k * m;
+                const float s = s_s[k];
+                if (s != 0.f) {
+                    const float c = s_c[k];
+                    const int p = s_p[k], q = s_q[k];
+                    const float x = S[p * P + j], y = S[q * P + j];
+                    S[p * P + j] = c * x - s * y;
+                    S[q * P + j] = s * x + c * y;
+                }
+            }
+            __syncthreads();
+        }
+        ++sweeps;
+        if (!s_flag) break;
+    }
+    __syncthreads();
+    if (tid < half && prev_p >= 0) { S[prev_p * P + prev_q] = 0.f; S[prev_q * P + prev_p] = 0.f; }
+    __syncthreads();
+    if (sig_out) *sig_out = s_sig;
+    return sweeps;
+}
+
+// ---------------------------------------------------------------------------
+// direct path: n <= 128, one CTA per matrix
+// ---------------------------------------------------------------------------
+struct DirectMat { const float* A; float* Q; float* d; int n; };
+
+__global__ void __launch_bounds__(512, 1)
+jacobi_direct_kernel(const DirectMat* mats, float eps_floor, int* sweeps_out, const int* out_index) {
+    extern __shared__ float smem[];
+    const DirectMat mt = mats[blockIdx.x];
+    const int n = mt.n, m = (n + 1) & ~1, P = m + 1;
+    float* S = smem;
+    float* U = smem + (size_t)m * P;
+    __shared__ float s_lam[DIRECT_MAX_N];
+    __shared__ int s_rank[DIRECT_MAX_N];
+    __shared__ float s_red[16];
+    const int tid = threadIdx.x, nt = blockDim.x;
+    float dmax = 0.f;
+    for (int e = tid; e < m * m; e += nt) {
+        const int i = e / m, j = e - i * m;
+        float v = 0.f;
+        if (i < n && j < n) v = 0.5f * (mt.A[(long)i * n + j] + mt.A[(long)j * n + i]);
+        S[i * P + j] = v;
+        U[i * P + j] = (i == j) ? 1.f : 0.f;
+        if (i == j) dmax = fmaxf(dmax, fabsf(v));
+    }
+    // max |diag| as the absolute scale
+    for (int o = 16; o > 0; o >>= 1) dmax = fmaxf(dmax, __shfl_xor_sync(0xffffffffu, dmax, o));
+    if ((tid & 31) == 0) s_red[tid >> 5] = dmax;
+    __syncthreads();
+    if (tid == 0) {
+        float v = 0.f;
+        for (int i = 0; i < (nt >> 5); ++i) v = fmaxf(v, s_red[i]);
+        s_red[0] = v;
+    }
+    __syncthreads();
+    const float scale = s_red[0];
+    __syncthreads();
+    const int sw = jacobi_smem(S, U, m, P, 1.2e-7f, 1.5e-8f * scale, 1e30f, 30, nullptr);
+    if (tid < n) s_lam[tid] = S[tid * P + tid];
+    __syncthreads();
+    if (tid < n) {
+        const float v = s_lam[tid];
+        int rk = 0;
+        for (int j = 0; j < n; ++j) {
+            const float w = s_lam[j];
+            rk += (w < v) || (w == v && j < tid);
+        }
+        s_rank[tid] = rk;
+        mt.d[rk] = v > eps_floor ? v : 0.f;
+    }
+    __syncthreads();
+    for (int e = tid; e < n * n; e += nt) {
+        const int i = e / n, j = e - i * n;      // eigenvector j, component i
+        mt.Q[(long)i * n + s_rank[j]] = U[i * P + j];
+    }
+    if (tid == 0 && sweeps_out) sweeps_out[out_index[blockIdx.x]] = sw;
+}
+
+// ---------------------------------------------------------------------------
+// blocked one-sided path
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ bool bj_pair_blocks(const BjMat& mt, int q, int round, int& bi, int& bj) {
+    const int pm1 = mt.p - 1;
+    const int r = round % pm1;
+    int a, b;
+    if (q == 0) { a = pm1; b = r; }
+    else { a = (r + q) % pm1; b = (r - q + pm1) % pm1; }
+    bi = min(a, b); bj = max(a, b);
+    return bj < mt.nblk;           // pairs with the dummy block idle this round
+}
+
+__global__ void bj_init_kernel(const BjMat* mats) {
+    const BjMat mt = mats[blockIdx.y];
+    const long ld = 2L * mt.n_pad;
+    const long tot = (long)mt.n_pad * ld;
+    for (long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < tot;
+         e += (long)gridDim.x * blockDim.x) {
+        const int i = (int)(e / ld), c = (int)(e - (long)i * ld);
+        float v;
+        if (c < mt.n_pad) v = (i < mt.n && c < mt.n) ? 0.5f * (mt.A[(long)i * mt.n + c] + mt.A[(long)c * mt.n + i]) : 0.f;
+        else v = (c - mt.n_pad == i) ? 1.f : 0.f;
+        mt.X[e] = v;
+    }
+}
+
+// Gram of the 64 W-rows of one pair over one k-chunk.  grid (total_pairs, max ksplit)
+__global__ void __launch_bounds__(256)
+bj_gram_kernel(const BjMat* mats, const int* pair_mat, const BjState* state, int round,
+               float* __restrict__ partial, const long* partial_off) {
+    __shared__ float xs[BK][BJ_M + 4];
+    const int mi = pair_mat[blockIdx.x];
+    const BjMat mt = mats[mi];
+    if (state[mi].converged || (int)blockIdx.y >= mt.ksplit) return;
+    int bi, bj;
+    if (!bj_pair_blocks(mt, blockIdx.x - mt.pair_begin, round, bi, bj)) return;
+    const long ld = 2L * mt.n_pad;
+    const int kbeg = blockIdx.y * BJ_KCHUNK, kend = min(mt.n_pad, kbeg + BJ_KCHUNK);
+    const int tid = threadIdx.x, kk = tid & 31, rr = tid >> 5;
+    const int tx = tid & 15, ty = tid >> 4;
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    const float* rowp[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int r = rr + 8 * i;
+        const int grow = (r < BJ_B) ? bi * BJ_B + r : bj * BJ_B + (r - BJ_B);
+        rowp[i] = mt.X + (long)grow * ld;
+    }
+    float reg[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) reg[i] = (kbeg + kk < kend) ? rowp[i][kbeg + kk] : 0.f;
+    for (int k0 = kbeg; k0 < kend; k0 += BK) {
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < 8; ++i) xs[kk][rr + 8 * i] = reg[i];
+        __syncthreads();
+        if (k0 + BK < kend) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) reg[i] = (k0 + BK + kk < kend) ? rowp[i][k0 + BK + kk] : 0.f;
+        }
+#pragma unroll
+        for (int k = 0; k < BK; ++k) {
+            const float4 a = *reinterpret_cast<const float4*>(&xs[k][ty * 4]);
+            const float4 b = *reinterpret_cast<const float4*>(&xs[k][tx * 4]);
+            const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+        }
+    }
+    float* dst = partial + partial_off[mi] +
+                 ((long)(blockIdx.x - mt.pair_begin) * mt.ksplit + blockIdx.y) * (BJ_M * BJ_M);
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+        *reinterpret_cast<float4*>(&dst[(ty * 4 + i) * BJ_M + tx * 4]) =
+            make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+}
+
+// inner eigenproblem: sum the Gram partials, Jacobi in shared memory, emit U.  grid total_pairs
+__global__ void __launch_bounds__(256)
+bj_solve_kernel(const BjMat* mats, const int* pair_mat, BjState* state, int round,
+                const float* __restrict__ partial, const long* partial_off,
+                float* __restrict__ ubuf) {
+    constexpr int P = BJ_M + 1;
+    __shared__ float S[BJ_M * P];
+    __shared__ float U[BJ_M * P];
+    const int mi = pair_mat[blockIdx.x];
+    const BjMat mt = mats[mi];
+    if (state[mi].converged) return;
+    int bi, bj;
+    if (!bj_pair_blocks(mt, blockIdx.x - mt.pair_begin, round, bi, bj)) return;
+    const int tid = threadIdx.x;
+    const float* src = partial + partial_off[mi] +
+                       (long)(blockIdx.x - mt.pair_begin) * mt.ksplit * (BJ_M * BJ_M);
+    for (int e = tid; e < BJ_M * BJ_M; e += blockDim.x) {
+        float s = 0.f;
+        for (int z = 0; z < mt.ksplit; ++z) s += src[(long)z * (BJ_M * BJ_M) + e];
+        const int i = e / BJ_M, j = e - i * BJ_M;
+        S[i * P + j] = s;
+        U[i * P + j] = (i == j) ? 1.f : 0.f;
+    }
+    __syncthreads();
+    int sig = 0;
+    jacobi_smem(S, U, BJ_M, P, 1.0e-7f, 1e-36f, mt.tol_conv, 10, &sig);
+    float* dst = ubuf + (long)blockIdx.x * (BJ_M * BJ_M);
+    for (int e = tid; e < BJ_M * BJ_M; e += blockDim.x) {
+        const int i = e / BJ_M, j = e - i * BJ_M;
+        dst[e] = U[i * P + j];
+    }
+    if (tid == 0 && sig) atomicAdd(&state[mi].rot, 1);
+}
+
+// rows <- U^T rows for the 64 rows of a pair, 128 columns per CTA.  grid (max col tiles, total_pairs)
+__global__ void __launch_bounds__(256)
+bj_update_kernel(const BjMat* mats, const int* pair_mat, const BjState* state, int round,
+                 const float* __restrict__ ubuf) {
+    extern __shared__ float smem[];
+    float (*us)[BJ_M] = reinterpret_cast<float (*)[BJ_M]>(smem);                 // [k][i]
+    float (*xs)[TILE] = reinterpret_cast<float (*)[TILE]>(smem + BJ_M * BJ_M);   // [k][c]
+    const int mi = pair_mat[blockIdx.y];
+    const BjMat mt = mats[mi];
+    const long ld = 2L * mt.n_pad;
+    const int c0 = blockIdx.x * TILE;
+    if (state[mi].converged || c0 >= ld) return;
+    int bi, bj;
+    if (!bj_pair_blocks(mt, blockIdx.y - mt.pair_begin, round, bi, bj)) return;
+    const int tid = threadIdx.x;
+    const float* usrc = ubuf + (long)blockIdx.y * (BJ_M * BJ_M);
+    for (int e = tid; e < BJ_M * BJ_M / 4; e += 256)
+        reinterpret_cast<float4*>(smem)[e] = reinterpret_cast<const float4*>(usrc)[e];
+    // X tile: 64 rows x 128 cols, float4 per thread (ld and c0 are multiples of 4)
+    for (int e = tid; e < BJ_M * TILE / 4; e += 256) {
+        const int r = e / (TILE / 4), c4 = e - r * (TILE / 4);
+        const int grow = (r < BJ_B) ? bi * BJ_B + r : bj * BJ_B + (r - BJ_B);
+        const int c = c0 + c4 * 4;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (c < ld) v = *reinterpret_cast<const float4*>(mt.X + (long)grow * ld + c);
+        *reinterpret_cast<float4*>(&xs[r][c4 * 4]) = v;
+    }
+    __syncthreads();
+    const int tx = tid & 15, ty = tid >> 4;          // ty: 4 output rows, tx: 8 output cols
+    float acc[4][8];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+#pragma unroll 8
+    for (int k = 0; k < BJ_M; ++k) {
+        const float4 a = *reinterpret_cast<const float4*>(&us[k][ty * 4]);
+        const float4 b0 = *reinterpret_cast<const float4*>(&xs[k][tx * 4]);
+        const float4 b1 = *reinterpret_cast<const float4*>(&xs[k][64 + tx * 4]);
+        const float av[4] = {a.x, a.y, a.z, a.w};
+        const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int r = ty * 4 + i;
+        const int grow = (r < BJ_B) ? bi * BJ_B + r : bj * BJ_B + (r - BJ_B);
+        float* dst = mt.X + (long)grow * ld + c0;
+        if (c0 + tx * 4 < ld)
+            *reinterpret_cast<float4*>(dst + tx * 4) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+        if (c0 + 64 + tx * 4 < ld)
+            *reinterpret_cast<float4*>(dst + 64 + tx * 4) = make_float4(acc[i][4], acc[i][5], acc[i][6], acc[i][7]);
+    }
+}
+
+// end-of-round bookkeeping: sweep boundaries, convergence flags, active count for the host
+__global__ void bj_check_kernel(const BjMat* mats, BjState* state, int nmat, int round,
+                                int max_sweeps, volatile int* host_active) {
+    __shared__ int active;
+    if (threadIdx.x == 0) active = 0;
+    __syncthreads();
+    for (int mi = threadIdx.x; mi < nmat; mi += blockDim.x) {
+        BjState st = state[mi];
+        if (!st.converged) {
+            const int pm1 = mats[mi].p - 1;
+            if ((round + 1) % pm1 == 0) {
+                st.sweeps += 1;
+                if (st.rot == 0 || st.sweeps >= max_sweeps) st.converged = 1;
+                st.rot = 0;
+                state[mi] = st;
+            }
+            if (!st.converged) atomicAdd(&active, 1);
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) *host_active = active;
+}
+
+// lam_i = (v_i . y_i) / (v_i . v_i) with y_i = A v_i stored in the W half.  one warp per row
+__global__ void bj_rayleigh_kernel(const BjMat* mats) {
+    const BjMat mt = mats[blockIdx.y];
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= mt.n) return;
+    const long ld = 2L * mt.n_pad;
+    const float* y = mt.X + (long)row * ld;
+    const float* v = y + mt.n_pad;
+    double num = 0.0, den = 0.0;
+    for (int c = threadIdx.x & 31; c < mt.n; c += 32) {
+        const float vv = v[c];
+        num += (double)vv * (double)y[c];
+        den += (double)vv * (double)vv;
+    }
+    num = warp_sum(num); den = warp_sum(den);
+    if ((threadIdx.x & 31) == 0) {
+        mt.lam[row] = (float)(num / den);
+        mt.nrm[row] = (float)den;
+    }
+}
+
+// ascending sort of the eigenvalues of one matrix (bitonic in shared memory), emits perm + d
+__global__ void __launch_bounds__(1024)
+bj_sort_kernel(const BjMat* mats, float eps_floor) {
+    extern __shared__ unsigned char raw[];
+    const BjMat mt = mats[blockIdx.x];
+    int np2 = 1;
+    while (np2 < mt.n) np2 <<= 1;
+    float* key = reinterpret_cast<float*>(raw);
+    int* idx = reinterpret_cast<int*>(raw + (size_t)np2 * sizeof(float));
+    for (int i = threadIdx.x; i < np2; i += blockDim.x) {
+        key[i] = i < mt.n ? mt.lam[i] : INFINITY;
+        idx[i] = i;
+    }
+    __syncthreads();
+    for (int k = 2; k <= np2; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = threadIdx.x; i < np2; i += blockDim.x) {
+                const int ixj = i ^ j;
+                if (ixj > i) {
+                    const bool up = (i & k) == 0;
+                    const float a = key[i], b = key[ixj];
+                    const int ia = idx[i], ib = idx[ixj];
+                    const bool gt = (a > b) || (a == b && ia > ib);
+                    if (gt == up) { key[i] = b; key[ixj] = a; idx[i] = ib; idx[ixj] = ia; }
+                }
+            }
+            __syncthreads();
+        }
+    }
+    for (int i = threadIdx.x; i < mt.n; i += blockDim.x) {
+        mt.perm[i] = idx[i];
+        const float v = key[i];
+        mt.d[i] = v > eps_floor ? v : 0.f;
+    }
+}
+
+// Q[r][c] = V[r, perm[c]] / ||v||  = X[perm[c]][n_pad + r] * rsqrt(nrm).  32x32 transpose tiles
+__global__ void bj_write_kernel(const BjMat* mats) {
+    __shared__ float t[32][33];
+    const BjMat mt = mats[blockIdx.z];
+    const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+    if (c0 >= mt.n || r0 >= mt.n) return;
+    const long ld = 2L * mt.n_pad;
+    const int lx = threadIdx.x & 31, ly = threadIdx.x >> 5;    // 256 threads: ly in [0,8)
+    for (int cc = ly; cc < 32; cc += 8) {
+        const int c = c0 + cc, r = r0 + lx;
+        float v = 0.f;
+        if (c < mt.n && r < mt.n) {
+            const int src = mt.perm[c];
+            v = mt.X[(long)src * ld + mt.n_pad + r] * rsqrtf(mt.nrm[src]);
+        }
+        t[cc][lx] = v;
+    }
+    __syncthreads();
+    for (int rr = ly; rr < 32; rr += 8) {
+        const int r = r0 + rr, c = c0 + lx;
+        if (r < mt.n && c < mt.n) mt.Q[(long)r * mt.n + c] = t[lx][rr];
+    }
+}
+
+__global__ void bj_store_sweeps_kernel(const BjState* state, const int* out_index, int nmat, int* sweeps_out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < nmat) sweeps_out[out_index[i]] = state[i].sweeps;
+}
+
+// epilogue of the Rayleigh GEMM: Y -> W half of X (row stride 2 n_pad)
+struct EpiToX {
+    float* X; long ld;
+    __device__ __forceinline__ void operator()(int m, int n, float v) const { X[(long)m * ld + n] = v; }
+};
+
+// ---------------------------------------------------------------------------
+// workspace plan
+// ---------------------------------------------------------------------------
+struct EighPlan {
+    int n_direct = 0, n_block = 0, total_pairs = 0, max_ksplit = 1, max_rounds = 0;
+    long max_ld = 0;
+    size_t off_dmats = 0, off_dindex = 0, off_bmats = 0, off_bindex = 0, off_pairmat = 0,
+           off_partoff = 0, off_state = 0, off_ubuf = 0, off_partial = 0, off_perm = 0,
+           off_lam = 0, off_x = 0, total = 0;
+};
+
+static int bj_npad(int n) { return cdiv(n, BJ_B) * BJ_B; }
+
+static EighPlan make_plan(const int32_t* n, int count) {
+    EighPlan pl;
+    size_t x_bytes = 0, part_floats = 0, lam_floats = 0, perm_ints = 0;
+    for (int i = 0; i < count; ++i) {
+        if (n[i] <= 0) continue;
+        if (n[i] <= DIRECT_MAX_N) { pl.n_direct++; continue; }
+        pl.n_block++;
+        const int np = bj_npad(n[i]);
+        const int nblk = np / BJ_B;
+        const int p = (nblk + 1) & ~1;
+        const int ks = cdiv(np, BJ_KCHUNK);
+        pl.total_pairs += p / 2;
+        if (ks > pl.max_ksplit) pl.max_ksplit = ks;
+        if ((p - 1) * BJ_MAX_SWEEPS > pl.max_rounds) pl.max_rounds = (p - 1) * BJ_MAX_SWEEPS;
+        if (2L * np > pl.max_ld) pl.max_ld = 2L * np;
+        x_bytes += align_up((size_t)np * 2 * np * sizeof(float), 256);
+        part_floats += (size_t)(p / 2) * ks * BJ_M * BJ_M;
+        lam_floats += 2 * (size_t)np;
+        perm_ints += (size_t)np;
+    }
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off += align_up(bytes, 256); return o; };
+    pl.off_dmats = take(sizeof(DirectMat) * (size_t)(pl.n_direct + 1));
+    pl.off_dindex = take(sizeof(int) * (size_t)(pl.n_direct + 1));
+    pl.off_bmats = take(sizeof(BjMat) * (size_t)(pl.n_block + 1));
+    pl.off_bindex = take(sizeof(int) * (size_t)(pl.n_block + 1));
+    pl.off_pairmat = take(sizeof(int) * (size_t)(pl.total_pairs + 1));
+    pl.off_partoff = take(sizeof(long) * (size_t)(pl.n_block + 1));
+    pl.off_state = take(sizeof(BjState) * (size_t)(pl.n_block + 1));
+    pl.off_ubuf = take(sizeof(float) * (size_t)pl.total_pairs * BJ_M * BJ_M);
+    pl.off_partial = take(sizeof(float) * part_floats);
+    pl.off_perm = take(sizeof(int) * perm_ints);
+    pl.off_lam = take(sizeof(float) * lam_floats);
+    pl.off_x = take(x_bytes);
+    pl.total = off + 256;
+    return pl;
+}
+
+static int* host_active_flag(int** dev_ptr) {
+    static int* h = nullptr;
+    static int* d = nullptr;
+    if (!h) {
+        if (cudaHostAlloc((void**)&h, sizeof(int), cudaHostAllocMapped) != cudaSuccess) return nullptr;
+        if (cudaHostGetDevicePointer((void**)&d, h, 0) != cudaSuccess) return nullptr;
+        *h = 1;
+    }
+    *dev_ptr = d;
+    return h;
+}
+
+}  // namespace kfacb
+
+using namespace kfacb;
+
+extern "C" size_t kfacb_eigh_workspace_bytes(const int32_t* n, int32_t count) {
+    return make_plan(n, count).total;
+}
+
+extern "C" int kfacb_eigh_batched(const int32_t* n, int32_t count,
+                                  const float* const* M, float* const* Q, float* const* d,
+                                  float eps_floor, int32_t* sweeps_out,
+                                  void* workspace, size_t workspace_bytes,
+                                  kfacb_stream_t stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    KFACB_REQUIRE(n && M && Q && d && count >= 0, "null argument");
+    const EighPlan pl = make_plan(n, count);
+    if (workspace_bytes < pl.total || ((uintptr_t)workspace & 255)) {
+        set_error("eigh workspace too small or misaligned (%zu < %zu)", workspace_bytes, pl.total);
+        return KFACB_ERR_WORKSPACE;
+    }
+    char* ws = (char*)workspace;
+
+    // ---- direct path ----
+    if (pl.n_direct > 0) {
+        DirectMat* hm = new DirectMat[pl.n_direct];
+        int* hidx = new int[pl.n_direct];
+        int k = 0, nmax = 0;
+        for (int i = 0; i < count; ++i) {
+            if (n[i] <= 0 || n[i] > DIRECT_MAX_N) continue;
+            if (!M[i] || !Q[i] || !d[i]) { delete[] hm; delete[] hidx; set_error("matrix %d: null pointer", i); return KFACB_ERR_ARG; }
+            hm[k] = DirectMat{M[i], Q[i], d[i], n[i]};
+            hidx[k] = i;
+            if (n[i] > nmax) nmax = n[i];
+            ++k;
+        }
+        cudaError_t e1 = cudaMemcpyAsync(ws + pl.off_dmats, hm, sizeof(DirectMat) * k, cudaMemcpyHostToDevice, st);
+        cudaError_t e2 = cudaMemcpyAsync(ws + pl.off_dindex, hidx, sizeof(int) * k, cudaMemcpyHostToDevice, st);
+        delete[] hm; delete[] hidx;
+        KFACB_CHECK_CUDA(e1); KFACB_CHECK_CUDA(e2);
+        const int m = (nmax + 1) & ~1;
+        const size_t smem = 2 * (size_t)m * (m + 1) * sizeof(float);
+        KFACB_CHECK_CUDA(cudaFuncSetAttribute(jacobi_direct_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const int threads = nmax <= 32 ? 128 : (nmax <= 64 ? 256 : 512);
+        jacobi_direct_kernel<<<k, threads, smem, st>>>((const DirectMat*)(ws + pl.off_dmats), eps_floor,
+                                                       sweeps_out, (const int*)(ws + pl.off_dindex));
+        KFACB_CHECK_LAUNCH();
+    }
+    if (pl.n_block == 0) return KFACB_OK;
+
+    // ---- blocked path ----
+    BjMat* hm = new BjMat[pl.n_block];
+    int* hidx = new int[pl.n_block];
+    long* hpoff = new long[pl.n_block];
+    int* hpm = new int[pl.total_pairs];
+    struct Guard { BjMat* a; int* b; long* c; int* d; ~Guard() { delete[] a; delete[] b; delete[] c; delete[] d; } } guard{hm, hidx, hpoff, hpm};
+    {
+        size_t xo = pl.off_x, lo = pl.off_lam, po = pl.off_perm;
+        long partial_off = 0;
+        int k = 0, pair = 0;
+        for (int i = 0; i < count; ++i) {
+            if (n[i] <= DIRECT_MAX_N) continue;
+            KFACB_REQUIRE(M[i] && Q[i] && d[i], "matrix %d: null pointer", i);
+            BjMat& b = hm[k];
+            b.n = n[i]; b.n_pad = bj_npad(n[i]); b.nblk = b.n_pad / BJ_B; b.p = (b.nblk + 1) & ~1;
+            b.A = M[i]; b.Q = Q[i]; b.d = d[i];
+            b.X = (float*)(ws + xo); xo += align_up((size_t)b.n_pad * 2 * b.n_pad * sizeof(float), 256);
+            b.lam = (float*)(ws + lo); b.nrm = b.lam + b.n_pad; lo += 2 * (size_t)b.n_pad * sizeof(float);
+            b.perm = (int*)(ws + po); po += (size_t)b.n_pad * sizeof(int);
+            b.pair_begin = pair; b.ksplit = cdiv(b.n_pad, BJ_KCHUNK);
+            const float t = 6e-8f * sqrtf((float)b.n);
+            b.tol_conv = t > 2e-6f ? t : 2e-6f;
+            hpoff[k] = partial_off;
+            partial_off += (long)(b.p / 2) * b.ksplit * BJ_M * BJ_M;
+            for (int q = 0; q < b.p / 2; ++q) hpm[pair++] = k;
+            hidx[k] = i;
+            ++k;
+        }
+    }
+    const int nb = pl.n_block;
+    KFACB_CHECK_CUDA(cudaMemcpyAsync(ws + pl.off_bmats, hm, sizeof(BjMat) * nb, cudaMemcpyHostToDevice, st));
+    KFACB_CHECK_CUDA(cudaMemcpyAsync(ws + pl.off_bindex, hidx, sizeof(int) * nb, cudaMemcpyHostToDevice, st));
+    KFACB_CHECK_CUDA(cudaMemcpyAsync(ws + pl.off_partoff, hpoff, sizeof(long) * nb, cudaMemcpyHostToDevice, st));
+    KFACB_CHECK_CUDA(cudaMemcpyAsync(ws + pl.off_pairmat, hpm, sizeof(int) * pl.total_pairs, cudaMemcpyHostToDevice, st));
+    KFACB_CHECK_CUDA(cudaMemsetAsync(ws + pl.off_state, 0, sizeof(BjState) * nb, st));
+    const BjMat* dm = (const BjMat*)(ws + pl.off_bmats);
+    const int* dpm = (const int*)(ws + pl.off_pairmat);
+    const long* dpoff = (const long*)(ws + pl.off_partoff);
+    BjState* dstate = (BjState*)(ws + pl.off_state);
+    float* ubuf = (float*)(ws + pl.off_ubuf);
+    float* partial = (float*)(ws + pl.off_partial);
+
+    int* d_active = nullptr;
+    int* h_active = host_active_flag(&d_active);
+    if (!h_active) { set_error("cannot allocate the pinned progress flag"); return KFACB_ERR_CUDA; }
+    *h_active = 1;
+
+    bj_init_kernel<<<dim3(4 * sm_count(), nb), 256, 0, st>>>(dm);
+    KFACB_CHECK_LAUNCH();
+
+    const size_t upd_smem = (size_t)(BJ_M * BJ_M + BJ_M * TILE) * sizeof(float);
+    KFACB_CHECK_CUDA(cudaFuncSetAttribute(bj_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)upd_smem));
+    const int col_tiles = cdiv(pl.max_ld, TILE);
+    constexpr int CH = 24;            // rounds per progress chunk (host look-ahead = 2 chunks)
+    cudaEvent_t ev[2];
+    KFACB_CHECK_CUDA(cudaEventCreateWithFlags(&ev[0], cudaEventDisableTiming));
+    KFACB_CHECK_CUDA(cudaEventCreateWithFlags(&ev[1], cudaEventDisableTiming));
+    int rc = KFACB_OK;
+    for (int r = 0; r < pl.max_rounds; ++r) {
+        if (r % CH == 0 && r >= 2 * CH) {
+            if (cudaEventSynchronize(ev[(r / CH) & 1]) != cudaSuccess) { rc = KFACB_ERR_CUDA; set_error("event sync failed"); break; }
+            if (*(volatile int*)h_active == 0) break;
+        }
+        bj_gram_kernel<<<dim3(pl.total_pairs, pl.max_ksplit), 256, 0, st>>>(dm, dpm, dstate, r, partial, dpoff);
+        bj_solve_kernel<<<pl.total_pairs, 256, 0, st>>>(dm, dpm, dstate, r, partial, dpoff, ubuf);
+        bj_update_kernel<<<dim3(col_tiles, pl.total_pairs), 256, upd_smem, st>>>(dm, dpm, dstate, r, ubuf);
+        bj_check_kernel<<<1, 256, 0, st>>>(dm, dstate, nb, r, BJ_MAX_SWEEPS, d_active);
+        if (cudaGetLastError() != cudaSuccess) { rc = KFACB_ERR_CUDA; set_error("jacobi round launch failed"); break; }
+        if (r % CH == CH - 1) cudaEventRecord(ev[(r / CH) & 1], st);
+    }
+    cudaEventDestroy(ev[0]); cudaEventDestroy(ev[1]);
+    if (rc) return rc;
+
+    // Rayleigh quotients: Y = V^T A  (row i of Y = A v_i), written over the W half
+    for (int k = 0; k < nb; ++k) {
+        const BjMat& b = hm[k];
+        LdKContig la{b.X + b.n_pad, 2L * b.n_pad, b.n, b.n};
+        LdMnContig lb{b.A, (long)b.n, b.n, b.n};
+        EpiToX epi{b.X, 2L * b.n_pad};
+        KFACB_CHECK_CUDA(launch_gemm(la, lb, epi, b.n, b.n, b.n, st));
+    }
+    int nmax = 0;
+    for (int k = 0; k < nb; ++k) if (hm[k].n > nmax) nmax = hm[k].n;
+    bj_rayleigh_kernel<<<dim3(cdiv(nmax, 8), nb), 256, 0, st>>>(dm);
+    KFACB_CHECK_LAUNCH();
+    int np2 = 1;
+    while (np2 < nmax) np2 <<= 1;
+    const size_t sort_smem = (size_t)np2 * 8;
+    KFACB_CHECK_CUDA(cudaFuncSetAttribute(bj_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sort_smem));
+    bj_sort_kernel<<<nb, 1024, sort_smem, st>>>(dm, eps_floor);
+    KFACB_CHECK_LAUNCH();
+    bj_write_kernel<<<dim3(cdiv(nmax, 32), cdiv(nmax, 32), nb), 256, 0, st>>>(dm);
+    KFACB_CHECK_LAUNCH();
+    if (sweeps_out) {
+        bj_store_sweeps_kernel<<<cdiv(nb, 128), 128, 0, st>>>(dstate, (const int*)(ws + pl.off_bindex), nb, sweeps_out);
+        KFACB_CHECK_LAUNCH();
+    }
+    return KFACB_OK;
+}

@@ -1,0 +1,275 @@
+// inverse.cu -- pi-damped SPD inverse (C-ABI: kfacb_pi_damped_inverse).
+// Replaces kfac/kfac_preconditioner_inv_dp.py:98-123, _add_value_to_diagonal
+// (kfac_preconditioner_inv.py:106-107) and mat_inv (kfac/utils.py:11-16:
+// cholesky + cholesky_inverse) of the reference.
+//
+// The inverse is computed by an in-place BLOCK GAUSS-JORDAN sweep without
+// pivoting (all pivots are Schur complements of an SPD matrix, hence SPD):
+// for each 64-wide diagonal block k
+//     D      = W_kk^-1                       (scalar Gauss-Jordan in shared memory)
+//     C      = -W[:,k] D                     (n x 64 panel, SIMT GEMM)
+//     W_ij  += C_i W_kj      (i,j != k)      (rank-64 update of the whole matrix, SIMT GEMM)
+//     W_kj   = D W_kj, W_ik = C_i, W_kk = D
+// After the last block W = M^-1; it is symmetrised on the way out (the
+// reference's cholesky_inverse result is exactly symmetric).
+#include "common.cuh"
+
+namespace kfacb {
+
+constexpr int GJ_NB = 64;
+
+struct DampJob { float* A; float* G; int nA, nG; };
+
+// pi = sqrt((tr A / dA) / (tr G / dG));  A += sqrt(damping)*pi I;  G += sqrt(damping)/pi I
+__global__ void pi_damp_kernel(const DampJob* jobs, float sqrt_damping) {
+    const DampJob jb = jobs[blockIdx.x];
+    __shared__ float red[2][8];
+    float ta = 0.f, tg = 0.f;
+    for (int i = threadIdx.x; i < jb.nA; i += blockDim.x) ta += jb.A[(long)i * jb.nA + i];
+    for (int i = threadIdx.x; i < jb.nG; i += blockDim.x) tg += jb.G[(long)i * jb.nG + i];
+    ta = warp_sum(ta); tg = warp_sum(tg);
+    if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = ta; red[1][threadIdx.x >> 5] = tg; }
+    __syncthreads();
+    ta = 0.f; tg = 0.f;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) { ta += red[0][i]; tg += red[1][i]; }
+    const float pi = sqrtf((ta / (float)jb.nA) / (tg / (float)jb.nG));
+    const float da = sqrt_damping * pi, dg = sqrt_damping / pi;
+    for (int i = threadIdx.x; i < jb.nA; i += blockDim.x) jb.A[(long)i * jb.nA + i] += da;
+    for (int i = threadIdx.x; i < jb.nG; i += blockDim.x) jb.G[(long)i * jb.nG + i] += dg;
+}
+
+// D = inverse of the nb x nb diagonal block at (k0, k0) of W (n x n).  one CTA, 256 threads
+__global__ void __launch_bounds__(256)
+gj_diag_kernel(const float* __restrict__ W, int n, int k0, int nb, float* __restrict__ D) {
+    __shared__ float a[GJ_NB][GJ_NB + 1];
+    __shared__ float colv[GJ_NB], rowv[GJ_NB];
+    const int tid = threadIdx.x;
+    for (int e = tid; e < GJ_NB * GJ_NB; e += 256) {
+        const int i = e / GJ_NB, j = e - i * GJ_NB;
+        a[i][j] = (i < nb && j < nb) ? W[(long)(k0 + i) * n + k0 + j] : (i == j ? 1.f : 0.f);
+    }
+    __syncthreads();
+    for (int s = 0; s < nb; ++s) {
+        const float piv = 1.f / a[s][s];
+        if (tid < GJ_NB) { colv[tid] = a[tid][s]; rowv[tid] = a[s][tid]; }
+        __syncthreads();
+        for (int e = tid; e < GJ_NB * GJ_NB; e += 256) {
+            const int i = e / GJ_NB, j = e - i * GJ_NB;
+            float v;
+            if (i == s && j == s) v = piv;
+            else if (i == s) v = rowv[j] * piv;
+            else if (j == s) v = -colv[i] * piv;
+            else v = a[i][j] - colv[i] * piv * rowv[j];
+            a[i][j] = v;
+        }
+        __syncthreads();
+    }
+    for (int e = tid; e < GJ_NB * GJ_NB; e += 256) {
+        const int i = e / GJ_NB, j = e - i * GJ_NB;
+        D[e] = a[i][j];
+    }
+}
+
+// whole-matrix path for n <= 64: out = M^-1 directly.  one CTA per matrix
+struct SmallInvJob { const float* M; float* out; int n; };
+__global__ void __launch_bounds__(256)
+gj_small_kernel(const SmallInvJob* jobs) {
+    const SmallInvJob jb = jobs[blockIdx.x];
+    __shared__ float a[GJ_NB][GJ_NB + 1];
+    __shared__ float colv[GJ_NB], rowv[GJ_NB];
+    const int tid = threadIdx.x, n = jb.n;
+    for (int e = tid; e < GJ_NB * GJ_NB; e += 256) {
+        const int i = e / GJ_NB, j = e - i * GJ_NB;
+        a[i][j] = (i < n && j < n) ? jb.M[(long)i * n + j] : (i == j ? 1.f : 0.f);
+    }
+    __syncthreads();
+    for (int s = 0; s < n; ++s) {
+        const float piv = 1.f / a[s][s];
+        if (tid < GJ_NB) { colv[tid] = a[tid][s]; rowv[tid] = a[s][tid]; }
+        __syncthreads();
+        for (int e = tid; e < GJ_NB * GJ_NB; e += 256) {
+            const int i = e / GJ_NB, j = e - i * GJ_NB;
+            float v;
+            if (i == s && j == s) v = piv;
+            else if (i == s) v = rowv[j] * piv;
+            else if (j == s) v = -colv[i] * piv;
+            else v = a[i][j] - colv[i] * piv * rowv[j];
+            a[i][j] = v;
+        }
+        __syncthreads();
+    }
+    for (int e = tid; e < n * n; e += 256) {
+        const int i = e / n, j = e - i * n;
+        jb.out[e] = 0.5f * (a[i][j] + a[j][i]);
+    }
+}
+
+// C[i][:] = -W[i][k0:k0+nb] D   for all rows i (rows inside block k are computed but unused)
+struct LdPanel {       // A operand (m = row i, kk): W[i*n + k0 + kk]
+    static constexpr bool K_FAST = true;
+    const float* W; int n, k0, nb;
+    __device__ __forceinline__ float operator()(int mn, int k) const {
+        return (mn < n && k < nb) ? W[(long)mn * n + k0 + k] : 0.f;
+    }
+};
+struct LdDcol {        // B operand (n = col c of D, kk): D[kk*64 + c]
+    static constexpr bool K_FAST = false;
+    const float* D; int nb;
+    __device__ __forceinline__ float operator()(int mn, int k) const {
+        return (mn < nb && k < nb) ? D[k * GJ_NB + mn] : 0.f;
+    }
+};
+struct EpiNegStore {
+    float* C;
+    __device__ __forceinline__ void operator()(int m, int n, float v) const { C[(long)m * GJ_NB + n] = -v; }
+};
+
+// rank-nb update: W[i][j] += sum_kk C[i][kk] W[k0+kk][j]   for i, j outside block k
+struct LdC {
+    static constexpr bool K_FAST = true;
+    const float* C; int n, nb;
+    __device__ __forceinline__ float operator()(int mn, int k) const {
+        return (mn < n && k < nb) ? C[(long)mn * GJ_NB + k] : 0.f;
+    }
+};
+struct LdRowBlk {
+    static constexpr bool K_FAST = false;
+    const float* W; int n, k0, nb;
+    __device__ __forceinline__ float operator()(int mn, int k) const {
+        return (mn < n && k < nb) ? W[(long)(k0 + k) * n + mn] : 0.f;
+    }
+};
+struct EpiRankUpdate {
+    float* W; int n, k0, nb;
+    __device__ __forceinline__ void operator()(int m, int c, float v) const {
+        if ((unsigned)(m - k0) < (unsigned)nb || (unsigned)(c - k0) < (unsigned)nb) return;
+        W[(long)m * n + c] += v;
+    }
+};
+
+// W[k rows][j] = D W[k rows][j] (j outside k);  W[i][k cols] = C[i] (i outside k);  W_kk = D
+__global__ void gj_fix_kernel(float* __restrict__ W, int n, int k0, int nb,
+                              const float* __restrict__ D, const float* __restrict__ C) {
+    __shared__ float ds[GJ_NB][GJ_NB + 1];
+    for (int e = threadIdx.x; e < GJ_NB * GJ_NB; e += blockDim.x) ds[e / GJ_NB][e % GJ_NB] = D[e];
+    __syncthreads();
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;     // column (row-block fix) / row (col-block fix)
+    if (j >= n) return;
+    const bool inside = (unsigned)(j - k0) < (unsigned)nb;
+    if (!inside) {
+        float old[GJ_NB];
+#pragma unroll 8
+        for (int s = 0; s < GJ_NB; ++s) old[s] = s < nb ? W[(long)(k0 + s) * n + j] : 0.f;
+        for (int r = 0; r < nb; ++r) {
+            float acc = 0.f;
+#pragma unroll 8
+            for (int s = 0; s < GJ_NB; ++s) acc = fmaf(ds[r][s], old[s], acc);
+            W[(long)(k0 + r) * n + j] = acc;
+        }
+        for (int c = 0; c < nb; ++c) W[(long)j * n + k0 + c] = C[(long)j * GJ_NB + c];
+    } else {
+        const int r = j - k0;
+        for (int c = 0; c < nb; ++c) W[(long)j * n + k0 + c] = ds[r][c];
+    }
+}
+
+__global__ void symmetrize_kernel(float* __restrict__ W, int n) {
+    const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long)n * n) return;
+    const int i = (int)(idx / n), j = (int)(idx - (long)i * n);
+    if (i < j) {
+        const float v = 0.5f * (W[idx] + W[(long)j * n + i]);
+        W[idx] = v;
+        W[(long)j * n + i] = v;
+    }
+}
+
+static size_t inv_scratch_bytes(int nmax) {
+    // D (64x64) + C (nmax x 64)
+    return align_up(GJ_NB * GJ_NB * sizeof(float), 256) + align_up((size_t)nmax * GJ_NB * sizeof(float), 256);
+}
+
+static int invert_large(const float* M, float* out, int n, float* D, float* C, cudaStream_t st) {
+    KFACB_CHECK_CUDA(cudaMemcpyAsync(out, M, (size_t)n * n * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    for (int k0 = 0; k0 < n; k0 += GJ_NB) {
+        const int nb = (n - k0 < GJ_NB) ? n - k0 : GJ_NB;
+        gj_diag_kernel<<<1, 256, 0, st>>>(out, n, k0, nb, D);
+        KFACB_CHECK_LAUNCH();
+        KFACB_CHECK_CUDA(launch_gemm(LdPanel{out, n, k0, nb}, LdDcol{D, nb}, EpiNegStore{C}, n, nb, nb, st));
+        KFACB_CHECK_CUDA(launch_gemm(LdC{C, n, nb}, LdRowBlk{out, n, k0, nb},
+                                     EpiRankUpdate{out, n, k0, nb}, n, n, nb, st));
+        gj_fix_kernel<<<cdiv(n, 128), 128, 0, st>>>(out, n, k0, nb, D, C);
+        KFACB_CHECK_LAUNCH();
+    }
+    symmetrize_kernel<<<cdiv((long)n * n, 256), 256, 0, st>>>(out, n);
+    KFACB_CHECK_LAUNCH();
+    return KFACB_OK;
+}
+
+}  // namespace kfacb
+
+using namespace kfacb;
+
+extern "C" size_t kfacb_spd_inverse_workspace_bytes(const int32_t* nA, const int32_t* nG, int32_t count) {
+    int nmax = 1;
+    for (int i = 0; i < count; ++i) {
+        if (nA[i] > nmax) nmax = nA[i];
+        if (nG[i] > nmax) nmax = nG[i];
+    }
+    return align_up(sizeof(DampJob) * (size_t)(count + 1), 256) +
+           align_up(sizeof(SmallInvJob) * (size_t)(2 * count + 1), 256) + inv_scratch_bytes(nmax) + 256;
+}
+
+extern "C" int kfacb_pi_damped_inverse(const int32_t* nA, const int32_t* nG, int32_t count,
+                                       float* const* A, float* const* G,
+                                       float* const* invA, float* const* invG,
+                                       float damping,
+                                       void* workspace, size_t workspace_bytes,
+                                       kfacb_stream_t stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    KFACB_REQUIRE(nA && nG && A && G && invA && invG && count >= 0, "null argument");
+    if (workspace_bytes < kfacb_spd_inverse_workspace_bytes(nA, nG, count) || ((uintptr_t)workspace & 255)) {
+        set_error("inverse workspace too small or misaligned");
+        return KFACB_ERR_WORKSPACE;
+    }
+    char* ws = (char*)workspace;
+    DampJob* djobs = (DampJob*)ws;
+    size_t off = align_up(sizeof(DampJob) * (size_t)(count + 1), 256);
+    SmallInvJob* sjobs = (SmallInvJob*)(ws + off);
+    off += align_up(sizeof(SmallInvJob) * (size_t)(2 * count + 1), 256);
+    float* D = (float*)(ws + off);
+    float* C = (float*)(ws + off + align_up(GJ_NB * GJ_NB * sizeof(float), 256));
+
+    DampJob* hd = new DampJob[count + 1];
+    SmallInvJob* hs = new SmallInvJob[2 * count + 1];
+    int nd = 0, ns = 0;
+    for (int i = 0; i < count; ++i) {
+        if (!A[i]) continue;
+        if (!G[i] || !invA[i] || !invG[i] || nA[i] <= 0 || nG[i] <= 0) {
+            delete[] hd; delete[] hs;
+            set_error("layer %d: null pointer or bad size", i);
+            return KFACB_ERR_ARG;
+        }
+        hd[nd++] = DampJob{A[i], G[i], nA[i], nG[i]};
+        if (nA[i] <= GJ_NB) hs[ns++] = SmallInvJob{A[i], invA[i], nA[i]};
+        if (nG[i] <= GJ_NB) hs[ns++] = SmallInvJob{G[i], invG[i], nG[i]};
+    }
+    cudaError_t e1 = cudaSuccess, e2 = cudaSuccess;
+    if (nd) e1 = cudaMemcpyAsync(djobs, hd, sizeof(DampJob) * nd, cudaMemcpyHostToDevice, st);
+    if (ns) e2 = cudaMemcpyAsync(sjobs, hs, sizeof(SmallInvJob) * ns, cudaMemcpyHostToDevice, st);
+    delete[] hd; delete[] hs;
+    KFACB_CHECK_CUDA(e1); KFACB_CHECK_CUDA(e2);
+    if (nd == 0) return KFACB_OK;
+    pi_damp_kernel<<<nd, 256, 0, st>>>(djobs, (float)sqrt((double)damping));
+    KFACB_CHECK_LAUNCH();
+    if (ns) {
+        gj_small_kernel<<<ns, 256, 0, st>>>(sjobs);
+        KFACB_CHECK_LAUNCH();
+    }
+    for (int i = 0; i < count; ++i) {
+        if (!A[i]) continue;
+        if (nA[i] > GJ_NB) { int rc = invert_large(A[i], invA[i], nA[i], D, C, st); if (rc) return rc; }
+        if (nG[i] > GJ_NB) { int rc = invert_large(G[i], invG[i], nG[i], D, C, st); if (rc) return rc; }
+    }
+    return KFACB_OK;
+}

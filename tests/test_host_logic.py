@@ -1,0 +1,186 @@
+"""CPU tests (no GPU): host orchestration of the product package driven through
+a TEST-ONLY oracle-backed engine, the C-ABI library's exported symbols, the
+scheduler and the backend shim."""
+import ctypes
+import os
+import re
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.multiprocessing as mp
+
+from tests.golden.cases import CASES, CASES_BY_NAME
+from tests.harness import compare_with_fixture, load_fixture, rel_err, run_package_case
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _fresh_backend():
+    from kfac_pytorch_b200 import backend
+    backend.comm = None
+    return backend
+
+
+@pytest.mark.parametrize('case', [c for c in CASES if c.world_size == 1], ids=lambda c: c.name)
+def test_orchestration_single_rank(case):
+    """KFAC.step() gating / EMA / identity init / pi-damping persistence / kl-clip
+    wiring, with the math supplied by the oracle: must reproduce the reference."""
+    from tests.oracle_engine import OracleEngine
+    _fresh_backend()
+    out, pre = run_package_case(case, torch.device('cpu'), engine=OracleEngine())
+    compare_with_fixture(case, out)
+    assert pre.steps == case.steps and pre.m_a == {} and pre.m_g == {}
+
+
+def _ws2_worker(rank, case_name, port, q):
+    sys.path.insert(0, ROOT)
+    import torch.distributed as dist
+    from tests.oracle_engine import OracleEngine
+    from kfac_pytorch_b200 import backend
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    os.environ['LOCAL_RANK'] = str(rank)
+    torch.set_num_threads(1)
+    dist.init_process_group('gloo', rank=rank, world_size=2)
+    backend.comm = None
+    backend.init('Torch')
+    case = CASES_BY_NAME[case_name]
+    out, pre = run_package_case(case, torch.device('cpu'), rank=rank, engine=OracleEngine())
+    q.put((rank, out, [r for r, _ in pre.module_ranks.values()]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize('case', [c for c in CASES if c.world_size == 2], ids=lambda c: c.name)
+def test_orchestration_world_size_2_gloo(case):
+    """Layer-partitioned run over 2 gloo ranks: round-robin ownership, owner-only
+    factors from the owner's local batch, slab exchange, identical grads on both ranks."""
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = 29700 + (abs(hash(case.name)) % 200)
+    procs = [ctx.Process(target=_ws2_worker, args=(r, case.name, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = {}
+    for _ in procs:
+        rank, out, owners = q.get(timeout=300)
+        res[rank] = out
+        assert owners == [i % 2 for i in range(len(owners))]
+    for p in procs:
+        p.join(timeout=60)
+    for rank in (0, 1):
+        compare_with_fixture(case, res[rank])
+    # all ranks end with bit-identical gradients
+    for k, v in res[0].items():
+        if k.endswith('wgrad') or k.endswith('bgrad'):
+            np.testing.assert_array_equal(v, res[1][k.replace('r0_', 'r1_', 1)])
+
+
+def test_c_abi_exports_every_declared_symbol():
+    """The shared library must load without a GPU and export everything
+    include/kfacb.h declares (no compute calls here)."""
+    from kfac_pytorch_b200 import build, native
+    build.build(verbose=False)
+    hdr = open(os.path.join(ROOT, 'include', 'kfacb.h')).read()
+    declared = set(re.findall(r'\b(kfacb_[a-z_A-Z0-9]+)\s*\(', hdr))
+    assert declared == set(native.EXPORTS), declared ^ set(native.EXPORTS)
+    lib = ctypes.CDLL(native.LIB_PATH)
+    for name in declared:
+        assert hasattr(lib, name), name
+    lib.kfacb_version.restype = ctypes.c_int
+    assert lib.kfacb_version() >= 100
+    d = native.LayerDesc()
+    d.kind, d.has_bias, d.in_c, d.out_c, d.kh, d.kw = native.KFACB_CONV2D, 1, 16, 24, 3, 3
+    lib.kfacb_layer_dA.argtypes = [ctypes.POINTER(native.LayerDesc)]
+    assert lib.kfacb_layer_dA(ctypes.byref(d)) == 145 == d.dA
+    assert native.load_library() is not None
+
+
+def test_step_fails_loudly_without_cuda():
+    import kfac_pytorch_b200 as kfac
+    _fresh_backend()
+    if torch.cuda.is_available():
+        pytest.skip('CUDA present')
+    model = torch.nn.Linear(4, 3)
+    pre = kfac.DP_KFAC(model)
+    model(torch.randn(2, 4)).sum().backward()
+    with pytest.raises(RuntimeError, match='no CPU fallback'):
+        pre.step()
+
+
+def test_api_surface_matches_reference():
+    import kfac
+    import kfac.backend as backend
+    assert list(kfac.kfac_mappers.keys()) == ['inverse', 'eigen', 'inverse_dp', 'eigen_dp']
+    assert kfac.get_kfac_module('eigen_dp') is kfac.kfac_mappers['eigen_dp']
+    assert kfac.get_kfac_module() is kfac.kfac_mappers['eigen_dp']
+    from kfac import DP_KFAC, KFACParamScheduler  # noqa: F401
+    backend.comm = None
+    model = torch.nn.Sequential(torch.nn.Linear(8, 4), torch.nn.LayerNorm(4), torch.nn.Linear(4, 30522))
+    pre = DP_KFAC(model, inv_type='eigen', exclude_vocabulary_size=30522, exclude_parts='CommunicateInverse')
+    assert isinstance(pre, torch.optim.Optimizer) and isinstance(pre, kfac.kfac_mappers['eigen_dp'])
+    assert len(pre.modules) == 1 and pre.module_names == ['module_name_Linear_0']
+    assert pre.exclude_communicate_inverse and not pre.exclude_compute_inverse
+    assert isinstance(DP_KFAC(model, inv_type='inverse'), kfac.kfac_mappers['inverse_dp'])
+    assert set(pre.param_groups[0]) >= {'lr', 'damping', 'fac_update_freq', 'kfac_update_freq'}
+    pre.set_hook_enabled(False)
+    assert pre.hook_enabled is False
+    for name in ('size', 'rank', 'local_rank', 'new_group', 'allreduce', 'allreduce_', 'allreduce_async_',
+                 'broadcast', 'broadcast_', 'broadcast_async_', 'synchronize', 'Average', 'Sum'):
+        assert hasattr(backend.comm, name), name
+    with pytest.raises(NotImplementedError):
+        kfac.get_kfac_module('eigen')(model)
+    backend.comm = None
+    with pytest.raises(RuntimeError):
+        backend.init('Torch')            # no process group: must RAISE (reference returns the error)
+
+
+def test_param_scheduler_semantics():
+    import kfac
+    _fresh_backend()
+    model = torch.nn.Linear(4, 3)
+    pre = kfac.DP_KFAC(model, damping=0.03, fac_update_freq=10, kfac_update_freq=100)
+    sched = kfac.KFACParamScheduler(pre, damping_alpha=0.5, damping_schedule=[2, 4],
+                                    update_freq_alpha=0.5, update_freq_schedule=[3], start_epoch=0)
+    seen = []
+    for _ in range(5):
+        sched.step()
+        g = pre.param_groups[0]
+        seen.append((sched.epoch, round(g['damping'], 6), g['fac_update_freq'], g['kfac_update_freq']))
+    assert seen == [(1, 0.03, 10, 100), (2, 0.015, 10, 100), (3, 0.015, 5, 50),
+                    (4, 0.0075, 5, 50), (5, 0.0075, 5, 50)]
+    sched.step(epoch=0)
+    assert pre.param_groups[0]['damping'] == 0.03
+    # LambdaLR drives lr through param_groups like any optimizer (reference: examples/pytorch_imagenet_resnet.py:318)
+    lrs = torch.optim.lr_scheduler.LambdaLR(pre, lambda e: 0.1 ** e)
+    pre.param_groups[0]['lr']
+    lrs.step()
+    assert abs(pre.param_groups[0]['lr'] - 0.01) < 1e-12
+
+
+def test_greedy_partition_balances_better_than_round_robin():
+    from kfac_pytorch_b200 import backend
+    import kfac_pytorch_b200 as kfac
+
+    class FakeComm(backend._SingleBackend):
+        def size(self):
+            return 4
+    backend.comm = FakeComm()
+    try:
+        dims = [(64, 64), (4608, 512), (64, 256), (4608, 512), (512, 2048), (4608, 512), (2048, 512), (2049, 1000)]
+        model = torch.nn.Sequential(*[torch.nn.Linear(a, g, bias=False) for a, g in dims])
+
+        def max_load(pre):
+            load = [0.0] * 4
+            for m in pre.modules:
+                load[pre.module_ranks[m][0]] += m.in_features ** 3 + m.out_features ** 3
+            return max(load)
+        rr = kfac.DP_KFAC(model)
+        gr = kfac.DP_KFAC(model, partition='greedy')
+        assert [r for r, _ in rr.module_ranks.values()] == [i % 4 for i in range(len(dims))]
+        assert all(a == g for a, g in gr.module_ranks.values())
+        assert max_load(gr) < max_load(rr)
+    finally:
+        backend.comm = None
