@@ -1,0 +1,394 @@
+#!/usr/bin/env python
+"""bench.py -- `preconditioner.step()` ms/iter on the BASELINE.json workload.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload resnet50] [--impl ours|reference]
+
+ours (default): the CUDA path through the drop-in Python API / C ABI.
+  * workload: ResNet-50 layer table, bs 32 per GPU, eigen_dp, fac_update_freq =
+    kfac_update_freq = 1, synthetic activations / output-gradients / parameter
+    gradients of the named shapes (N(0,1), N(0,1)/B, N(0,1)),
+    injected with hook_enabled=False and RE-DRAWN every step from a pool of
+    pre-generated input sets, so the factors (and their eigenbases) really change
+    from step to step.
+  * `value`: ms per step with inputs resident in HBM (CUDA events over K steps,
+    barrier + synchronize on both sides, max over ranks).
+  * `e2e`: the same step driven from pinned HOST buffers: per step H2D of every
+    owned a / g and of all gradients, step(), D2H of all rewritten gradients.
+  * `roofline`: the dominant phase of the step (eigendecomposition) against the
+    tensor roofline, F = sum 9 n^3; all phases are listed
+    under `phases`.
+  * `cpu_baseline`: the oracle (CPU restatement of the reference) on this box's
+    host cores on a bounded sample (one layer per distinct shape class, scaled by
+    class multiplicity).
+
+reference (--impl reference): the reference's own CPU algorithm (oracle port; the
+  reference is pure Python/PyTorch and is not present on the GPU box) on the host
+  cores, same workload / metric / unit; every step is the bounded class sample.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = 'preconditioner.step() ms/iter (ResNet-50, bs=32/gpu)'
+
+
+def load_peaks():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        with open(p) as fh:
+            d = json.load(fh)
+        return dict(hbm=d.get('hbm_gbs', 6650.0), bf16=d.get('bf16_tflops', 1590.0),
+                    bf16_sustained=d.get('bf16_tflops_sustained', 1400.0), src='measured')
+    return dict(hbm=6650.0, bf16=1590.0, bf16_sustained=1400.0, src='fallback')
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons during the timed region."""
+    Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,'
+         'clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, gpu_index=0):
+        self.gpu, self.rows, self.proc = gpu_index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ['nvidia-smi', '-i', str(self.gpu), '--query-gpu=' + self.Q,
+                 '--format=csv,noheader,nounits', '-lms', '200'],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(',')])
+
+    def stop(self):
+        if self.proc is None:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=['nvidia-smi unavailable'])
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm = sorted(float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace('.', '').isdigit())
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace('.', '').isdigit()]
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        reasons = sorted({n for r in self.rows if len(r) >= 9
+                          for n, v in zip(names, r[5:9]) if v.lower().startswith('active')})
+        return dict(sm_mhz=sm[len(sm) // 2] if sm else None, sm_max_mhz=max(mx) if mx else None,
+                    reasons=reasons, samples=len(sm))
+
+
+# ---------------------------------------------------------------------------
+# CPU arm: oracle on a bounded sample
+# ---------------------------------------------------------------------------
+def cpu_class_sample(workload: str, batch: int, variant: str, hyper: dict, repeats: int = 1):
+    """One layer per distinct shape class through the oracle's full per-layer
+    pipeline (factors + EMA, eigh / inverse, two-sided product, KL-clip rewrite),
+    timed individually and scaled by the class multiplicity.
+    Returns (estimated full-step seconds, seconds of CPU work actually done, description)."""
+    from oracle.kfac_oracle import OracleDPKFAC, specs_from_model, synth_grads, synth_layer_inputs
+    from kfac_pytorch_b200.workloads import WORKLOADS, LayerStack, io_shapes
+    layers = WORKLOADS[workload][0]()
+    classes = {}
+    for ls in layers:
+        spec = specs_from_model(LayerStack([ls.module]))[0][0]
+        key = (spec.kind, spec.dA, spec.dG, io_shapes(ls, batch))
+        classes.setdefault(key, [ls, spec, 0])
+        classes[key][2] += 1
+    torch.set_num_threads(os.cpu_count() or 1)
+    est, spent = 0.0, 0.0
+    for key, (ls, spec, count) in classes.items():
+        gen = torch.Generator().manual_seed(1234)
+        li = synth_layer_inputs(spec, batch, ls.hw, ls.seq, gen)
+        w, b = synth_grads(spec, gen)
+        orc = OracleDPKFAC([spec], variant=variant, lr=hyper['lr'], damping=hyper['damping'],
+                           kl_clip=hyper['kl_clip'])
+        t0 = time.perf_counter()
+        for _ in range(repeats):
+            orc.step([[li]], [w], [b])
+        dt = (time.perf_counter() - t0) / repeats
+        est += dt * count
+        spent += dt * repeats
+    desc = ('%d distinct layer shape classes of %d layers, one layer per class through the full '
+            'per-layer pipeline, time scaled by class multiplicity' % (len(classes), len(layers)))
+    return est, spent, desc
+
+
+def run_reference(args):
+    from kfac_pytorch_b200.workloads import WORKLOADS
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    _, variant, batch, hyper = WORKLOADS[args.workload]
+    for _ in range(args.warmup):
+        cpu_class_sample(args.workload, batch, variant, hyper)
+    t0 = time.perf_counter()
+    ests = []
+    for _ in range(args.steps):
+        est, spent, desc = cpu_class_sample(args.workload, batch, variant, hyper)
+        ests.append(est)
+    wall = time.perf_counter() - t0
+    value = 1e3 * sum(ests) / len(ests)
+    cores = os.cpu_count() or 1
+    line = dict(impl='reference', metric=METRIC, value=value, unit='ms', n_gpus=args.gpus,
+                steps=args.steps, warmup=args.warmup, ms_per_step=value, higher_is_better=False,
+                scaling='weak', vs_baseline=None, dtype='f32', data='synthetic',
+                config=dict(workload=args.workload, variant=variant, batch_per_gpu=batch,
+                            note='reference algorithm (oracle port) on host CPU; rank 0 only'),
+                cpu_baseline=dict(value=value, unit='ms', cores=cores, kind='port',
+                                  sample=desc + '; sample wall per step %.1f s' % (wall / max(1, args.steps))),
+                e2e=dict(value=value, unit='ms', h2d_bytes_per_step=0, d2h_bytes_per_step=0),
+                gpu_launches=0)
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------
+# CUDA arm
+# ---------------------------------------------------------------------------
+def run_ours(args):
+    import torch.distributed as dist
+    import kfac_pytorch_b200 as kfac
+    from kfac_pytorch_b200 import backend
+    from kfac_pytorch_b200.workloads import (WORKLOADS, LayerStack, algorithmic_work, io_shapes)
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py: no CUDA device (the hot path has no CPU fallback); '
+                         'use --impl reference for the CPU arm')
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+        backend.comm = None
+        backend.init('Torch')
+    table_fn, variant, batch, hyper = WORKLOADS[args.workload]
+    layers = table_fn()
+    model = LayerStack([ls.module for ls in layers]).to(dev)
+    pre = kfac.get_kfac_module(variant)(model, lr=hyper['lr'], damping=hyper['damping'],
+                                        kl_clip=hyper['kl_clip'], factor_decay=0.95,
+                                        fac_update_freq=1, kfac_update_freq=1, hook_enabled=False,
+                                        partition=args.partition)
+    mods = pre.modules
+    assert len(mods) == len(layers)
+    owned = [i for i, m in enumerate(mods) if pre.module_ranks[m][0] == rank]
+
+    # ---- synthetic inputs (device resident), NSETS different draws ----
+    gen = torch.Generator(device=dev).manual_seed(1234 + rank)
+    ggen = torch.Generator(device=dev).manual_seed(999)
+    nsets = args.input_sets
+    a_sets = [dict() for _ in range(nsets)]
+    g_sets = [dict() for _ in range(nsets)]
+    for k in range(nsets):
+        for i in owned:
+            sa, sg = io_shapes(layers[i], batch)
+            a_sets[k][i] = torch.randn(*sa, device=dev, generator=gen)
+            g_sets[k][i] = torch.randn(*sg, device=dev, generator=gen) / batch
+    wmaster = [torch.randn_like(m.weight, memory_format=torch.contiguous_format) for m in mods]
+    bmaster = [None if m.bias is None else torch.randn_like(m.bias) for m in mods]
+    for i, m in enumerate(mods):          # identical on all ranks (post all-reduce gradients)
+        wmaster[i] = torch.randn(m.weight.shape, device=dev, generator=ggen)
+        if m.bias is not None:
+            bmaster[i] = torch.randn(m.bias.shape, device=dev, generator=ggen)
+        m.weight.grad = torch.empty_like(m.weight)
+        if m.bias is not None:
+            m.bias.grad = torch.empty_like(m.bias)
+
+    def inject(k):
+        for i in owned:
+            pre.m_a[mods[i]] = a_sets[k][i]
+            pre.m_g[mods[i]] = g_sets[k][i]
+        for i, m in enumerate(mods):
+            m.weight.grad.copy_(wmaster[i])
+            if m.bias is not None:
+                m.bias.grad.copy_(bmaster[i])
+
+    # ---- phase timers (CUDA events on the launching stream) ----
+    phase_names = ['_compute_factors', '_compute_inverse', '_compute_pred', '_communicate_pred',
+                   '_update_grad_in_place']
+    phase_events = {n: [] for n in phase_names}
+    recording = {'on': False}
+
+    def wrap(name):
+        fn = getattr(pre, name)
+
+        def timed(*a, **kw):
+            if not recording['on']:
+                return fn(*a, **kw)
+            e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+            e0.record()
+            r = fn(*a, **kw)
+            e1.record()
+            phase_events[name].append((e0, e1))
+            return r
+        setattr(pre, name, timed)
+    for n in phase_names:
+        wrap(n)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+
+    def timed_loop(step_fn, steps):
+        barrier(); torch.cuda.synchronize()
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for s in range(steps):
+            step_fn(s)
+        e1.record()
+        torch.cuda.synchronize(); barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    def dev_step(s):
+        inject(s % nsets)
+        pre.step()
+
+    for s in range(args.warmup):
+        dev_step(s)
+    eng = pre._get_engine()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = eng.launch_count()
+    recording['on'] = True
+    total_ms = timed_loop(dev_step, args.steps)
+    recording['on'] = False
+    launches = eng.launch_count() - l0
+    clocks = sampler.stop() if rank == 0 else None
+    ms_per_step = total_ms / args.steps
+    phases = {}
+    for n, evs in phase_events.items():
+        if evs:
+            phases[n.strip('_')] = sum(a.elapsed_time(b) for a, b in evs) / len(evs)
+
+    # ---- e2e: host buffers, H2D + step + D2H inside the timed region ----
+    host_a = {i: a_sets[0][i].cpu().pin_memory() for i in owned}
+    host_g = {i: g_sets[0][i].cpu().pin_memory() for i in owned}
+    host_w = [w.cpu().pin_memory() for w in wmaster]
+    host_b = [None if b is None else b.cpu().pin_memory() for b in bmaster]
+    out_w = [torch.empty_like(h).pin_memory() for h in host_w]
+    out_b = [None if h is None else torch.empty_like(h).pin_memory() for h in host_b]
+    h2d = sum(t.numel() * 4 for t in list(host_a.values()) + list(host_g.values()) + host_w
+              + [b for b in host_b if b is not None])
+    d2h = sum(t.numel() * 4 for t in out_w + [b for b in out_b if b is not None])
+    dst_a, dst_g = a_sets[0], g_sets[0]
+
+    def e2e_step(s):
+        for i in owned:
+            dst_a[i].copy_(host_a[i], non_blocking=True)
+            dst_g[i].copy_(host_g[i], non_blocking=True)
+            pre.m_a[mods[i]] = dst_a[i]
+            pre.m_g[mods[i]] = dst_g[i]
+        for i, m in enumerate(mods):
+            m.weight.grad.copy_(host_w[i], non_blocking=True)
+            if m.bias is not None:
+                m.bias.grad.copy_(host_b[i], non_blocking=True)
+        pre.step()
+        for i, m in enumerate(mods):
+            out_w[i].copy_(m.weight.grad, non_blocking=True)
+            if m.bias is not None:
+                out_b[i].copy_(m.bias.grad, non_blocking=True)
+
+    e2e_step(0)
+    e2e_steps = max(1, min(args.steps, args.e2e_steps))
+    e2e_ms = timed_loop(e2e_step, e2e_steps) / e2e_steps
+
+    # ---- roofline of the dominant phase ----
+    peaks = load_peaks()
+    owned_layers = [layers[i] for i in owned]
+    work = algorithmic_work(owned_layers, batch, variant)
+    if world > 1:       # report the max-loaded rank's work alongside the max-over-ranks time
+        wt = torch.tensor([float(work['F_inverse'])], device=dev)
+        dist.all_reduce(wt, op=dist.ReduceOp.MAX)
+        work['F_inverse'] = float(wt.item())
+    tf32_peak = peaks['bf16_sustained'] / 2.0
+    inv_ms = phases.get('compute_inverse')
+    roofline = None
+    if inv_ms:
+        ach = work['F_inverse'] / (inv_ms * 1e-3) / 1e12
+        roofline = dict(bound='tensor', kernel='eigendecomposition phase (blocked Jacobi kernels)',
+                        achieved=ach, peak=tf32_peak, unit='TFLOP/s', frac=ach / tf32_peak,
+                        traffic=None,
+                        peak_note='dense TF32 = 1/2 of the %s sustained bf16 cuBLAS peak in '
+                                  'MEASURED_PEAKS.json; algorithmic flops = sum 9 n^3' % peaks['src'])
+    phase_report = {}
+    for name, key_f, key_b in (('compute_factors', 'F_factor', 'B_factor'),
+                               ('compute_inverse', 'F_inverse', 'B_inverse'),
+                               ('compute_pred', 'F_apply', 'B_apply'),
+                               ('update_grad_in_place', None, 'B_finalize')):
+        if name in phases:
+            ms = phases[name]
+            ent = dict(ms=ms)
+            if key_f:
+                ent['tflops'] = work[key_f] / (ms * 1e-3) / 1e12
+            ent['gbs'] = work[key_b] / (ms * 1e-3) / 1e9
+            phase_report[name] = ent
+    if 'communicate_pred' in phases:
+        phase_report['communicate_pred'] = dict(ms=phases['communicate_pred'])
+
+    # ---- CPU baseline (rank 0, N = 1 only) ----
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        est, spent, desc = cpu_class_sample(args.workload, batch, variant, hyper)
+        cpu = dict(value=est * 1e3, unit='ms', cores=os.cpu_count() or 1, kind='port',
+                   sample=desc + '; %.1f s of CPU work' % spent)
+
+    if rank == 0:
+        line = dict(metric=METRIC, value=ms_per_step, unit='ms', n_gpus=world, steps=args.steps,
+                    warmup=args.warmup, ms_per_step=ms_per_step, higher_is_better=False,
+                    scaling='weak', vs_baseline=None, dtype='f32', data='synthetic',
+                    config=dict(workload='%s bs=%d/gpu %s fac_update_freq=1 kfac_update_freq=1'
+                                         % (args.workload, batch, variant),
+                                partition=args.partition, layers=len(layers), input_sets=nsets,
+                                l2='inputs (2.8 GB a+g per set) and factors (615 MB) exceed the 126 MB L2',
+                                parallelism='layer-partitioned dp%d' % world),
+                    e2e=dict(value=e2e_ms, unit='ms', h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
+                             steps=e2e_steps),
+                    gpu_launches=int(launches), clocks=clocks, roofline=roofline,
+                    phases=phase_report, cpu_baseline=cpu, impl='ours')
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=5)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--workload', default='resnet50', choices=['resnet50', 'vgg16', 'bert_base', 'mlp'])
+    ap.add_argument('--partition', default='round_robin', choices=['round_robin', 'greedy'])
+    ap.add_argument('--input-sets', type=int, default=2)
+    ap.add_argument('--e2e-steps', type=int, default=3)
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    if args.impl == 'reference':
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == '__main__':
+    main()

@@ -73,6 +73,8 @@ int32_t kfacb_layer_dA(const kfacb_layer_t* l);
 int32_t kfacb_layer_dG(const kfacb_layer_t* l);
 
 int         kfacb_version(void);
+/* number of CUDA kernels this library has launched in this process (monotonic; for benchmarking) */
+uint64_t    kfacb_launch_count(void);
 const char* kfacb_last_error(void);
 /* fills SM count and compute capability of the current device */
 int         kfacb_device_info(int32_t* sm_count, int32_t* cc_major, int32_t* cc_minor);

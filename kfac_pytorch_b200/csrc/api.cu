@@ -14,6 +14,9 @@ void set_error(const char* fmt, ...) {
     va_end(ap);
 }
 
+static unsigned long long g_launches = 0;
+void count_launch(int n) { __atomic_fetch_add(&g_launches, (unsigned long long)n, __ATOMIC_RELAXED); }
+
 int sm_count() {
     static int cached[64] = {0};
     int dev = 0;
@@ -29,6 +32,8 @@ int sm_count() {
 }  // namespace kfacb
 
 extern "C" int kfacb_version(void) { return 100; }   /* 0.1.0 */
+
+extern "C" uint64_t kfacb_launch_count(void) { return __atomic_load_n(&kfacb::g_launches, __ATOMIC_RELAXED); }
 
 extern "C" const char* kfacb_last_error(void) { return kfacb::g_err; }
 

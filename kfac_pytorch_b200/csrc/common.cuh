@@ -26,7 +26,10 @@ void set_error(const char* fmt, ...);
         }                                                                          \
     } while (0)
 
-#define KFACB_CHECK_LAUNCH() KFACB_CHECK_CUDA(cudaGetLastError())
+void count_launch(int n = 1);   // kernels launched by this library (reported by bench.py)
+
+#define KFACB_CHECK_LAUNCH()                                                       \
+    do { ::kfacb::count_launch(); KFACB_CHECK_CUDA(cudaGetLastError()); } while (0)
 
 #define KFACB_REQUIRE(cond, ...)                                                   \
     do {                                                                           \
@@ -189,6 +192,7 @@ static inline cudaError_t launch_gemm(const LA& la, const LB& lb, const Epi& epi
                                       int M, int N, int K, cudaStream_t st, int batch = 1) {
     dim3 grid(cdiv(N, TILE), cdiv(M, TILE), batch);
     gemm_kernel<LA, LB, Epi><<<grid, GEMM_THREADS, 0, st>>>(la, lb, epi, M, N, K);
+    count_launch();
     return cudaGetLastError();
 }
 

@@ -661,6 +661,7 @@ extern "C" int kfacb_eigh_batched(const int32_t* n, int32_t count,
         bj_solve_kernel<<<pl.total_pairs, 256, 0, st>>>(dm, dpm, dstate, r, partial, dpoff, ubuf);
         bj_update_kernel<<<dim3(col_tiles, pl.total_pairs), 256, upd_smem, st>>>(dm, dpm, dstate, r, ubuf);
         bj_check_kernel<<<1, 256, 0, st>>>(dm, dstate, nb, r, BJ_MAX_SWEEPS, d_active);
+        count_launch(4);
         if (cudaGetLastError() != cudaSuccess) { rc = KFACB_ERR_CUDA; set_error("jacobi round launch failed"); break; }
         if (r % CH == CH - 1) cudaEventRecord(ev[(r / CH) & 1], st);
     }

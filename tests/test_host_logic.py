@@ -84,7 +84,7 @@ def test_c_abi_exports_every_declared_symbol():
     from kfac_pytorch_b200 import build, native
     build.build(verbose=False)
     hdr = open(os.path.join(ROOT, 'include', 'kfacb.h')).read()
-    declared = set(re.findall(r'\b(kfacb_[a-z_A-Z0-9]+)\s*\(', hdr))
+    declared = set(re.findall(r'^\s*(?:int|size_t|int32_t|uint64_t|const char\*)\s+(kfacb_\w+)\s*\(', hdr, re.M))
     assert declared == set(native.EXPORTS), declared ^ set(native.EXPORTS)
     lib = ctypes.CDLL(native.LIB_PATH)
     for name in declared:
