@@ -98,6 +98,36 @@ class ClockSampler:
 # ---------------------------------------------------------------------------
 # CPU arm: oracle on a bounded sample
 # ---------------------------------------------------------------------------
+_CPU_THREADS = None
+
+
+def pick_cpu_threads():
+    """LAPACK/MKL eigh does not scale to every hardware thread of a big host (128 threads
+    on this pool's boxes are ~100x SLOWER than 16 on a 1024^2 eigh).  Calibrate once on a
+    small problem and use the fastest setting: that is the best the CPU arm can do."""
+    global _CPU_THREADS
+    if _CPU_THREADS is not None:
+        return _CPU_THREADS
+    ncpu = os.cpu_count() or 1
+    x = torch.randn(2048, 768, generator=torch.Generator().manual_seed(0))
+    m = x.t() @ x / 2048
+    best, best_t = 1, float('inf')
+    for nt in sorted({ncpu, ncpu // 2, 32, 16, 8, 4}):
+        if nt < 1 or nt > ncpu:
+            continue
+        torch.set_num_threads(nt)
+        torch.linalg.eigh(m)
+        t0 = time.perf_counter()
+        torch.linalg.eigh(m)
+        x.t() @ x
+        dt = time.perf_counter() - t0
+        if dt < best_t:
+            best, best_t = nt, dt
+    _CPU_THREADS = best
+    torch.set_num_threads(best)
+    return best
+
+
 def cpu_class_sample(workload: str, batch: int, variant: str, hyper: dict, repeats: int = 1):
     """One layer per distinct shape class through the oracle's full per-layer
     pipeline (factors + EMA, eigh / inverse, two-sided product, KL-clip rewrite),
@@ -112,7 +142,7 @@ def cpu_class_sample(workload: str, batch: int, variant: str, hyper: dict, repea
         key = (spec.kind, spec.dA, spec.dG, io_shapes(ls, batch))
         classes.setdefault(key, [ls, spec, 0])
         classes[key][2] += 1
-    torch.set_num_threads(os.cpu_count() or 1)
+    pick_cpu_threads()
     est, spent = 0.0, 0.0
     for key, (ls, spec, count) in classes.items():
         gen = torch.Generator().manual_seed(1234)
@@ -146,7 +176,7 @@ def run_reference(args):
         ests.append(est)
     wall = time.perf_counter() - t0
     value = 1e3 * sum(ests) / len(ests)
-    cores = os.cpu_count() or 1
+    cores = pick_cpu_threads()
     line = dict(impl='reference', metric=METRIC, value=value, unit='ms', n_gpus=args.gpus,
                 steps=args.steps, warmup=args.warmup, ms_per_step=value, higher_is_better=False,
                 scaling='weak', vs_baseline=None, dtype='f32', data='synthetic',
@@ -351,8 +381,8 @@ def run_ours(args):
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         est, spent, desc = cpu_class_sample(args.workload, batch, variant, hyper)
-        cpu = dict(value=est * 1e3, unit='ms', cores=os.cpu_count() or 1, kind='port',
-                   sample=desc + '; %.1f s of CPU work' % spent)
+        cpu = dict(value=est * 1e3, unit='ms', cores=pick_cpu_threads(), kind='port',
+                   sample=desc + '; %.1f s of CPU work; %d of %d host threads (fastest setting found)' % (spent, pick_cpu_threads(), os.cpu_count() or 1))
 
     if rank == 0:
         line = dict(metric=METRIC, value=ms_per_step, unit='ms', n_gpus=world, steps=args.steps,

@@ -18,6 +18,7 @@
 //              are then recomputed as Rayleigh quotients v^T A v (second-order
 //              accurate), sorted ascending, floored, and V is written out
 //              column-wise.
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace kfacb {
@@ -26,6 +27,7 @@ constexpr int BJ_B = 32;              // rows per block
 constexpr int BJ_M = 2 * BJ_B;        // rows per pair = size of the inner eigenproblem
 constexpr int BJ_KCHUNK = 256;        // Gram split-K chunk
 constexpr int BJ_MAX_SWEEPS = 16;
+constexpr int BJ_INNER_SWEEPS = 10;   // cap of Jacobi sweeps on the 64x64 Gram per visit
 constexpr int DIRECT_MAX_N = 128;
 
 struct BjMat {
@@ -51,16 +53,18 @@ struct BjState {          // per matrix, device
 
 // ---------------------------------------------------------------------------
 // two-sided cyclic Jacobi on an m x m symmetric matrix in shared memory
-// (m even, pitch P odd).  On exit S is diagonal (to tolerance) and U holds the
+// (m even, pitch P odd; M_CT = m at compile time or 0).  On exit S is diagonal (to tolerance) and U holds the
 // accumulated rotations (columns = eigenvectors of the input).  Returns the
 // number of sweeps executed; *sig_out = 1 if any rotation exceeded sig_tol.
 // All threads of the CTA must call it.
 // ---------------------------------------------------------------------------
-__device__ int jacobi_smem(float* S, float* U, int m, int P, float tol_rel, float abs_thr,
+template <int M_CT>
+__device__ int jacobi_smem(float* S, float* U, int m_rt, int P, float tol_rel, float abs_thr,
                            float sig_tol, int max_sweeps, int* sig_out) {
     __shared__ float s_c[DIRECT_MAX_N / 2], s_s[DIRECT_MAX_N / 2];
     __shared__ int s_p[DIRECT_MAX_N / 2], s_q[DIRECT_MAX_N / 2];
     __shared__ int s_flag, s_sig;
+    const int m = M_CT ? M_CT : m_rt;            // compile-time size for the 64x64 inner problem
     const int tid = threadIdx.x, nt = blockDim.x;
     const int half = m >> 1, mm1 = m - 1;
     if (tid == 0) s_sig = 0;
@@ -75,16 +79,17 @@ __device__ int jacobi_smem(float* S, float* U, int m, int P, float tol_rel, floa
                 if (prev_p >= 0) { S[prev_p * P + prev_q] = 0.f; S[prev_q * P + prev_p] = 0.f; prev_p = -1; }
                 int p, q;
                 if (tid == 0) { p = mm1; q = r; }
-                else { p = (r + tid) % mm1; q = (r - tid + mm1) % mm1; }
+                else { p = r + tid; if (p >= mm1) p -= mm1; q = r - tid; if (q < 0) q += mm1; }
                 if (p > q) { const int t = p; p = q; q = t; }
                 const float app = S[p * P + p], aqq = S[q * P + q], apq = S[p * P + q];
                 float c = 1.f, s = 0.f;
                 const float mag = fabsf(apq);
                 const float ref = sqrtf(fabsf(app) * fabsf(aqq));
                 if (mag > tol_rel * ref && mag > abs_thr) {
+                    // Rutishauser's stable formulas; correctly rounded sqrt/div keep c^2+s^2 = 1 to ~1 ulp
                     const float tau = (aqq - app) / (2.f * apq);
                     const float t = (tau >= 0.f ? 1.f : -1.f) / (fabsf(tau) + sqrtf(1.f + tau * tau));
-                    c = rsqrtf(1.f + t * t);
+                    c = 1.f / sqrtf(1.f + t * t);
                     s = t * c;
                     s_flag = 1;
                     if (mag > sig_tol * ref) s_sig = 1;
@@ -93,7 +98,7 @@ __device__ int jacobi_smem(float* S, float* U, int m, int P, float tol_rel, floa
                 s_c[tid] = c; s_s[tid] = s; s_p[tid] = p; s_q[tid] = q;
             }
             __syncthreads();
-            // column rotations: S <- S J, U <- U J
+            // column rotations: S <- S J, U <- U J   (lanes walk the row index: conflict-free, P odd)
             for (int e = tid; e < half * m; e += nt) {
                 const int k = e / m, i = e - k * m;
                 const float s = s_s[k];
@@ -170,8 +175,28 @@ jacobi_direct_kernel(const DirectMat* mats, float eps_floor, int* sweeps_out, co
     __syncthreads();
     const float scale = s_red[0];
     __syncthreads();
-    const int sw = jacobi_smem(S, U, m, P, 1.2e-7f, 1.5e-8f * scale, 1e30f, 30, nullptr);
-    if (tid < n) s_lam[tid] = S[tid * P + tid];
+    const int sw = jacobi_smem<0>(S, U, m, P, 1.2e-7f, 1.5e-8f * scale, 1e30f, 30, nullptr);
+    // Eigenvalues as Rayleigh quotients of the ORIGINAL matrix: Y = A U (into S), lam_j = u_j.y_j / u_j.u_j.
+    // This is second-order accurate in the eigenvector error and immune to drift of diag(S).
+    __syncthreads();
+    for (int e = tid; e < n * n; e += nt) {
+        const int i = e / n, j = e - i * n;
+        float acc = 0.f;
+        for (int k = 0; k < n; ++k) acc = fmaf(__ldg(mt.A + (long)i * n + k), U[k * P + j], acc);
+        S[i * P + j] = acc;
+    }
+    __syncthreads();
+    __shared__ float s_nrm[DIRECT_MAX_N];
+    if (tid < n) {
+        double num = 0.0, den = 0.0;
+        for (int i = 0; i < n; ++i) {
+            const double u = U[i * P + tid];
+            num += u * (double)S[i * P + tid];
+            den += u * u;
+        }
+        s_lam[tid] = (float)(num / den);
+        s_nrm[tid] = (float)(1.0 / sqrt(den));
+    }
     __syncthreads();
     if (tid < n) {
         const float v = s_lam[tid];
@@ -186,7 +211,7 @@ jacobi_direct_kernel(const DirectMat* mats, float eps_floor, int* sweeps_out, co
     __syncthreads();
     for (int e = tid; e < n * n; e += nt) {
         const int i = e / n, j = e - i * n;      // eigenvector j, component i
-        mt.Q[(long)i * n + s_rank[j]] = U[i * P + j];
+        mt.Q[(long)i * n + s_rank[j]] = U[i * P + j] * s_nrm[j];
     }
     if (tid == 0 && sweeps_out) sweeps_out[out_index[blockIdx.x]] = sw;
 }
@@ -279,7 +304,7 @@ bj_gram_kernel(const BjMat* mats, const int* pair_mat, const BjState* state, int
 __global__ void __launch_bounds__(256)
 bj_solve_kernel(const BjMat* mats, const int* pair_mat, BjState* state, int round,
                 const float* __restrict__ partial, const long* partial_off,
-                float* __restrict__ ubuf) {
+                float* __restrict__ ubuf, int inner_sweeps) {
     constexpr int P = BJ_M + 1;
     __shared__ float S[BJ_M * P];
     __shared__ float U[BJ_M * P];
@@ -300,7 +325,7 @@ bj_solve_kernel(const BjMat* mats, const int* pair_mat, BjState* state, int roun
     }
     __syncthreads();
     int sig = 0;
-    jacobi_smem(S, U, BJ_M, P, 1.0e-7f, 1e-36f, mt.tol_conv, 10, &sig);
+    jacobi_smem<BJ_M>(S, U, BJ_M, P, 1.0e-7f, 1e-36f, mt.tol_conv, inner_sweeps, &sig);
     float* dst = ubuf + (long)blockIdx.x * (BJ_M * BJ_M);
     for (int e = tid; e < BJ_M * BJ_M; e += blockDim.x) {
         const int i = e / BJ_M, j = e - i * BJ_M;
@@ -493,6 +518,11 @@ struct EighPlan {
            off_lam = 0, off_x = 0, total = 0;
 };
 
+static int env_int(const char* name, int dflt) {
+    const char* v = getenv(name);
+    return (v && *v) ? atoi(v) : dflt;
+}
+
 static int bj_npad(int n) { return cdiv(n, BJ_B) * BJ_B; }
 
 static EighPlan make_plan(const int32_t* n, int count) {
@@ -508,7 +538,7 @@ static EighPlan make_plan(const int32_t* n, int count) {
         const int ks = cdiv(np, BJ_KCHUNK);
         pl.total_pairs += p / 2;
         if (ks > pl.max_ksplit) pl.max_ksplit = ks;
-        if ((p - 1) * BJ_MAX_SWEEPS > pl.max_rounds) pl.max_rounds = (p - 1) * BJ_MAX_SWEEPS;
+        if ((p - 1) * 64 > pl.max_rounds) pl.max_rounds = (p - 1) * 64;   // hard cap; the device-side sweep limit ends earlier
         if (2L * np > pl.max_ld) pl.max_ld = 2L * np;
         x_bytes += align_up((size_t)np * 2 * np * sizeof(float), 256);
         part_floats += (size_t)(p / 2) * ks * BJ_M * BJ_M;
@@ -652,15 +682,17 @@ extern "C" int kfacb_eigh_batched(const int32_t* n, int32_t count,
     KFACB_CHECK_CUDA(cudaEventCreateWithFlags(&ev[0], cudaEventDisableTiming));
     KFACB_CHECK_CUDA(cudaEventCreateWithFlags(&ev[1], cudaEventDisableTiming));
     int rc = KFACB_OK;
+    const int inner_sweeps = env_int("KFACB_INNER_SWEEPS", BJ_INNER_SWEEPS);   // tuning knobs
+    const int max_sweeps = env_int("KFACB_MAX_SWEEPS", BJ_MAX_SWEEPS);
     for (int r = 0; r < pl.max_rounds; ++r) {
         if (r % CH == 0 && r >= 2 * CH) {
             if (cudaEventSynchronize(ev[(r / CH) & 1]) != cudaSuccess) { rc = KFACB_ERR_CUDA; set_error("event sync failed"); break; }
             if (*(volatile int*)h_active == 0) break;
         }
         bj_gram_kernel<<<dim3(pl.total_pairs, pl.max_ksplit), 256, 0, st>>>(dm, dpm, dstate, r, partial, dpoff);
-        bj_solve_kernel<<<pl.total_pairs, 256, 0, st>>>(dm, dpm, dstate, r, partial, dpoff, ubuf);
+        bj_solve_kernel<<<pl.total_pairs, 256, 0, st>>>(dm, dpm, dstate, r, partial, dpoff, ubuf, inner_sweeps);
         bj_update_kernel<<<dim3(col_tiles, pl.total_pairs), 256, upd_smem, st>>>(dm, dpm, dstate, r, ubuf);
-        bj_check_kernel<<<1, 256, 0, st>>>(dm, dstate, nb, r, BJ_MAX_SWEEPS, d_active);
+        bj_check_kernel<<<1, 256, 0, st>>>(dm, dstate, nb, r, max_sweeps, d_active);
         count_launch(4);
         if (cudaGetLastError() != cudaSuccess) { rc = KFACB_ERR_CUDA; set_error("jacobi round launch failed"); break; }
         if (r % CH == CH - 1) cudaEventRecord(ev[(r / CH) & 1], st);

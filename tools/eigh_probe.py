@@ -1,0 +1,55 @@
+"""GPU probe: time kfacb_eigh_batched on Wishart matrices of the ResNet-50 factor
+sizes and report sweeps / accuracy.  Tuning knobs come from the environment
+(KFACB_INNER_SWEEPS, KFACB_MAX_SWEEPS).   python tools/eigh_probe.py 4608 [2304 ...]"""
+import os
+import sys
+import time
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from kfac_pytorch_b200.native import NativeEngine  # noqa: E402
+
+
+def wishart(n, rows, gen, dev):
+    x = torch.randn(rows, n, device=dev, generator=gen)
+    a = x.t() @ x / rows
+    return (0.05 * torch.eye(n, device=dev) + 0.95 * a).contiguous()
+
+
+def main():
+    dev = torch.device('cuda:0')
+    eng = NativeEngine(dev)
+    ns = [int(x) for x in sys.argv[1:]] or [4608]
+    gen = torch.Generator(device=dev).manual_seed(0)
+    mats = [wishart(n, max(1568, 2 * n) if n < 4608 else 1568, gen, dev) for n in ns]
+    Qs = [torch.empty_like(m) for m in mats]
+    ds = [torch.empty(m.shape[0], device=dev) for m in mats]
+    sw = torch.zeros(len(ns), dtype=torch.int32, device=dev)
+    for it in range(2):
+        torch.cuda.synchronize()
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        l0 = eng.launch_count()
+        e0.record()
+        eng.eigh(mats, Qs, ds, 1e-10, sw)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+    out = ['inner=%s max=%s ns=%s ms=%.1f launches=%d sweeps=%s' % (
+        os.environ.get('KFACB_INNER_SWEEPS', 'dflt'), os.environ.get('KFACB_MAX_SWEEPS', 'dflt'), ns, ms,
+        eng.launch_count() - l0, sw.tolist())]
+    for m, q, d in zip(mats, Qs, ds):
+        n = m.shape[0]
+        if n <= 2304:
+            ref = torch.linalg.eigvalsh(m.double())
+            derr = (d.double() - ref).abs().max().item() / ref.abs().max().item()
+        else:
+            derr = float('nan')
+        orth = (q.t() @ q - torch.eye(n, device=dev)).abs().max().item()
+        rec = ((q * d) @ q.t() - m).norm().item() / m.norm().item()
+        out.append('  n=%d eig_err=%.2e orth=%.2e recon=%.2e' % (n, derr, orth, rec))
+    print('\n'.join(out), flush=True)
+
+
+if __name__ == '__main__':
+    main()
