@@ -20,6 +20,7 @@
 //              column-wise.
 #include <stdlib.h>
 #include "common.cuh"
+#include "tc.cuh"
 
 namespace kfacb {
 
@@ -42,10 +43,11 @@ struct BjMat {
     int nblk;             // real number of blocks
     int pair_begin;       // first global pair index of this matrix
     int ksplit;           // Gram split-K factor
-    float tol_conv;       // relative off-diagonal size that still counts as "not converged"
+    float tol_conv;       // |h_pq| / max|diag A| that still counts as "not converged"
 };
 
 struct BjState {          // per matrix, device
+    int scale_bits;       // float bits of max |diag(A)| (absolute scale for the thresholds)
     int converged;
     int rot;              // significant rotations in the current sweep
     int sweeps;
@@ -55,12 +57,12 @@ struct BjState {          // per matrix, device
 // two-sided cyclic Jacobi on an m x m symmetric matrix in shared memory
 // (m even, pitch P odd; M_CT = m at compile time or 0).  On exit S is diagonal (to tolerance) and U holds the
 // accumulated rotations (columns = eigenvectors of the input).  Returns the
-// number of sweeps executed; *sig_out = 1 if any rotation exceeded sig_tol.
+// number of sweeps executed; *sig_out = 1 if any rotated element exceeded sig_abs.
 // All threads of the CTA must call it.
 // ---------------------------------------------------------------------------
 template <int M_CT>
 __device__ int jacobi_smem(float* S, float* U, int m_rt, int P, float tol_rel, float abs_thr,
-                           float sig_tol, int max_sweeps, int* sig_out) {
+                           float sig_abs, int max_sweeps, int* sig_out) {
     __shared__ float s_c[DIRECT_MAX_N / 2], s_s[DIRECT_MAX_N / 2];
     __shared__ int s_p[DIRECT_MAX_N / 2], s_q[DIRECT_MAX_N / 2];
     __shared__ int s_flag, s_sig;
@@ -92,7 +94,7 @@ __device__ int jacobi_smem(float* S, float* U, int m_rt, int P, float tol_rel, f
                     c = 1.f / sqrtf(1.f + t * t);
                     s = t * c;
                     s_flag = 1;
-                    if (mag > sig_tol * ref) s_sig = 1;
+                    if (mag > sig_abs) s_sig = 1;
                     prev_p = p; prev_q = q;
                 }
                 s_c[tid] = c; s_s[tid] = s; s_p[tid] = p; s_q[tid] = q;
@@ -229,8 +231,12 @@ __device__ __forceinline__ bool bj_pair_blocks(const BjMat& mt, int q, int round
     return bj < mt.nblk;           // pairs with the dummy block idle this round
 }
 
-__global__ void bj_init_kernel(const BjMat* mats) {
+__global__ void bj_init_kernel(const BjMat* mats, BjState* state) {
     const BjMat mt = mats[blockIdx.y];
+    float dmax = 0.f;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < mt.n; i += gridDim.x * blockDim.x)
+        dmax = fmaxf(dmax, fabsf(mt.A[(long)i * mt.n + i]));
+    if (dmax > 0.f) atomicMax(&state[blockIdx.y].scale_bits, __float_as_int(dmax));
     const long ld = 2L * mt.n_pad;
     const long tot = (long)mt.n_pad * ld;
     for (long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < tot;
@@ -243,11 +249,13 @@ __global__ void bj_init_kernel(const BjMat* mats) {
     }
 }
 
-// Gram of the 64 W-rows of one pair over one k-chunk.  grid (total_pairs, max ksplit)
+// Projected block H = V_R^T A V_R = V_R W_R^T (64x64) of one pair over one k-chunk (SIMT
+// fp32 version; the tensor-core version is bj_h_tc_kernel).  grid (total_pairs, max ksplit)
 __global__ void __launch_bounds__(256)
 bj_gram_kernel(const BjMat* mats, const int* pair_mat, const BjState* state, int round,
                float* __restrict__ partial, const long* partial_off) {
-    __shared__ float xs[BK][BJ_M + 4];
+    __shared__ float vs[BK][BJ_M + 4];
+    __shared__ float ws[BK][BJ_M + 4];
     const int mi = pair_mat[blockIdx.x];
     const BjMat mt = mats[mi];
     if (state[mi].converged || (int)blockIdx.y >= mt.ksplit) return;
@@ -269,22 +277,22 @@ bj_gram_kernel(const BjMat* mats, const int* pair_mat, const BjState* state, int
         const int grow = (r < BJ_B) ? bi * BJ_B + r : bj * BJ_B + (r - BJ_B);
         rowp[i] = mt.X + (long)grow * ld;
     }
-    float reg[8];
+    float rw[8], rv[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) reg[i] = (kbeg + kk < kend) ? rowp[i][kbeg + kk] : 0.f;
+    for (int i = 0; i < 8; ++i) { rw[i] = rowp[i][kbeg + kk]; rv[i] = rowp[i][mt.n_pad + kbeg + kk]; }
     for (int k0 = kbeg; k0 < kend; k0 += BK) {
         __syncthreads();
 #pragma unroll
-        for (int i = 0; i < 8; ++i) xs[kk][rr + 8 * i] = reg[i];
+        for (int i = 0; i < 8; ++i) { ws[kk][rr + 8 * i] = rw[i]; vs[kk][rr + 8 * i] = rv[i]; }
         __syncthreads();
         if (k0 + BK < kend) {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) reg[i] = (k0 + BK + kk < kend) ? rowp[i][k0 + BK + kk] : 0.f;
+            for (int i = 0; i < 8; ++i) { rw[i] = rowp[i][k0 + BK + kk]; rv[i] = rowp[i][mt.n_pad + k0 + BK + kk]; }
         }
 #pragma unroll
         for (int k = 0; k < BK; ++k) {
-            const float4 a = *reinterpret_cast<const float4*>(&xs[k][ty * 4]);
-            const float4 b = *reinterpret_cast<const float4*>(&xs[k][tx * 4]);
+            const float4 a = *reinterpret_cast<const float4*>(&vs[k][ty * 4]);
+            const float4 b = *reinterpret_cast<const float4*>(&ws[k][tx * 4]);
             const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
 #pragma unroll
             for (int i = 0; i < 4; ++i)
@@ -298,6 +306,215 @@ bj_gram_kernel(const BjMat* mats, const int* pair_mat, const BjState* state, int
     for (int i = 0; i < 4; ++i)
         *reinterpret_cast<float4*>(&dst[(ty * 4 + i) * BJ_M + tx * 4]) =
             make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+}
+
+// ---------------------------------------------------------------------------
+// tensor-core (tcgen05, 3xTF32) versions of the two GEMMs of a Jacobi round
+// ---------------------------------------------------------------------------
+constexpr int TC_THREADS = 128;
+// H kernel: K-major operands, 64-k slabs.  element (m, k): (m&7)*16 + (m>>3)*128 + (k>>2)*LBO + (k&3)*4
+constexpr int H_SLAB = 64;
+constexpr int H_LBO = 8 * 128 + 16;                 // +16 B pad: conflict-free staging stores
+constexpr int H_SBO = 128;
+constexpr int H_PART = (H_SLAB / 4) * H_LBO;        // bytes of one operand part (hi or lo)
+constexpr int H_SMEM = 4 * H_PART;
+
+__global__ void __launch_bounds__(TC_THREADS)
+bj_h_tc_kernel(const BjMat* mats, const int* pair_mat, const BjState* state, int round,
+               float* __restrict__ partial, const long* partial_off) {
+    extern __shared__ __align__(128) unsigned char dsm[];
+    __shared__ __align__(8) uint64_t mbar;
+    __shared__ uint32_t tmem_slot;
+    const int mi = pair_mat[blockIdx.x];
+    const BjMat mt = mats[mi];
+    if (state[mi].converged || (int)blockIdx.y >= mt.ksplit) return;
+    int bi, bj;
+    if (!bj_pair_blocks(mt, blockIdx.x - mt.pair_begin, round, bi, bj)) return;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (tid == 0) { tc::mbar_init(&mbar, 1); tc::fence_mbar_init(); }
+    if (warp == 0) tc::tmem_alloc<64>(&tmem_slot);
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tmem = tmem_slot;
+    unsigned char* a_hi = dsm;                    // V rows
+    unsigned char* a_lo = dsm + H_PART;
+    unsigned char* b_hi = dsm + 2 * H_PART;       // W rows
+    unsigned char* b_lo = dsm + 3 * H_PART;
+    const long ld = 2L * mt.n_pad;
+    const int kbeg = blockIdx.y * BJ_KCHUNK, kend = min(mt.n_pad, kbeg + BJ_KCHUNK);
+    const int nslab = (kend - kbeg + H_SLAB - 1) / H_SLAB;
+    constexpr uint32_t idesc = tc::idesc_tf32(64, 64, 0, 0);
+    for (int s = 0; s < nslab; ++s) {
+        const int k0 = kbeg + s * H_SLAB;
+        float4 va[8], wa[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int idx = tid + TC_THREADS * i;
+            const int kq = idx & 15, r = idx >> 4;
+            const int grow = (r < BJ_B) ? bi * BJ_B + r : bj * BJ_B + (r - BJ_B);
+            const float* base = mt.X + (long)grow * ld + k0 + kq * 4;
+            const bool ok = k0 + kq * 4 < kend;
+            wa[i] = ok ? *reinterpret_cast<const float4*>(base) : make_float4(0.f, 0.f, 0.f, 0.f);
+            va[i] = ok ? *reinterpret_cast<const float4*>(base + mt.n_pad) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        if (s > 0) tc::mbar_wait(&mbar, (uint32_t)((s - 1) & 1));   // MMAs of the previous slab done reading smem
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int idx = tid + TC_THREADS * i;
+            const int kq = idx & 15, r = idx >> 4;
+            const int off = (r & 7) * 16 + (r >> 3) * H_SBO + kq * H_LBO;
+            float4 hi, lo;
+            tc::split_tf32(va[i], hi, lo);
+            *reinterpret_cast<float4*>(a_hi + off) = hi;
+            *reinterpret_cast<float4*>(a_lo + off) = lo;
+            tc::split_tf32(wa[i], hi, lo);
+            *reinterpret_cast<float4*>(b_hi + off) = hi;
+            *reinterpret_cast<float4*>(b_lo + off) = lo;
+        }
+        tc::fence_async_smem();
+        __syncthreads();
+        if (tid == 0) {
+            tc::tc_fence_after();
+            const uint32_t ah = tc::smem_u32(a_hi), al = tc::smem_u32(a_lo);
+            const uint32_t bh = tc::smem_u32(b_hi), bl = tc::smem_u32(b_lo);
+#pragma unroll
+            for (int pass = 0; pass < 3; ++pass) {
+                const uint32_t ab = pass == 1 ? al : ah;
+                const uint32_t bb = pass == 2 ? bl : bh;
+#pragma unroll
+                for (int j = 0; j < H_SLAB / 8; ++j) {
+                    const uint64_t ad = tc::smem_desc(ab + 2 * j * H_LBO, H_LBO, H_SBO);
+                    const uint64_t bd = tc::smem_desc(bb + 2 * j * H_LBO, H_LBO, H_SBO);
+                    tc::umma_tf32(tmem, ad, bd, idesc, !(s == 0 && pass == 0 && j == 0));
+                }
+            }
+            tc::umma_commit(&mbar);
+        }
+    }
+    tc::mbar_wait(&mbar, (uint32_t)((nslab - 1) & 1));
+    tc::tc_fence_after();
+    // D (64x64, M=64 layout): row m lives in TMEM lane (m & 15) + 32 * (m >> 4)
+    float v0[32], v1[32];
+    const uint32_t taddr = tmem + ((uint32_t)(32 * warp) << 16);
+    tc::tmem_ld32(taddr, v0);
+    tc::tmem_ld32(taddr + 32, v1);
+    if (lane < 16) {
+        float* dst = partial + partial_off[mi] +
+                     ((long)(blockIdx.x - mt.pair_begin) * mt.ksplit + blockIdx.y) * (BJ_M * BJ_M) +
+                     (16 * warp + lane) * BJ_M;
+#pragma unroll
+        for (int c = 0; c < 32; c += 4) {
+            *reinterpret_cast<float4*>(dst + c) = make_float4(v0[c], v0[c + 1], v0[c + 2], v0[c + 3]);
+            *reinterpret_cast<float4*>(dst + 32 + c) = make_float4(v1[c], v1[c + 1], v1[c + 2], v1[c + 3]);
+        }
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tc::tmem_dealloc<64>(tmem);
+}
+
+// update kernel (transposed product): D[c][i] = sum_k X[r_k][c] U[k][i]; M = 128 columns of X,
+// N = 64, K = 64.  Both operands MN-major: (mn, k): (mn&3)*4 + (k&7)*16 + (mn>>2)*SBO + (k>>3)*LBO
+constexpr int U_SBO = 128 + 16;                     // +16 B pad: conflict-free staging stores
+constexpr int U_LBO_A = (TILE / 4) * U_SBO;         // 4608
+constexpr int U_LBO_B = (BJ_M / 4) * U_SBO;         // 2304
+constexpr int U_PART_A = (BJ_M / 8) * U_LBO_A;      // 36864
+constexpr int U_PART_B = (BJ_M / 8) * U_LBO_B;      // 18432
+constexpr int U_SMEM = 2 * U_PART_A + 2 * U_PART_B; // 110592
+
+__global__ void __launch_bounds__(TC_THREADS)
+bj_update_tc_kernel(const BjMat* mats, const int* pair_mat, const BjState* state, int round,
+                    const float* __restrict__ ubuf) {
+    extern __shared__ __align__(128) unsigned char dsm[];
+    __shared__ __align__(8) uint64_t mbar;
+    __shared__ uint32_t tmem_slot;
+    const int mi = pair_mat[blockIdx.y];
+    const BjMat mt = mats[mi];
+    const long ld = 2L * mt.n_pad;
+    const int c0 = blockIdx.x * TILE;
+    if (state[mi].converged || c0 >= ld) return;
+    int bi, bj;
+    if (!bj_pair_blocks(mt, blockIdx.y - mt.pair_begin, round, bi, bj)) return;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (tid == 0) { tc::mbar_init(&mbar, 1); tc::fence_mbar_init(); }
+    if (warp == 0) tc::tmem_alloc<64>(&tmem_slot);
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tmem = tmem_slot;
+    unsigned char* a_hi = dsm;
+    unsigned char* a_lo = dsm + U_PART_A;
+    unsigned char* b_hi = dsm + 2 * U_PART_A;
+    unsigned char* b_lo = dsm + 2 * U_PART_A + U_PART_B;
+    // X tile: 64 rows x 128 cols
+#pragma unroll 4
+    for (int i = 0; i < 16; ++i) {
+        const int idx = tid + TC_THREADS * i;
+        const int c4 = idx & 31, k = idx >> 5;
+        const int grow = (k < BJ_B) ? bi * BJ_B + k : bj * BJ_B + (k - BJ_B);
+        const int c = c0 + c4 * 4;
+        float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (c < ld) x = *reinterpret_cast<const float4*>(mt.X + (long)grow * ld + c);
+        float4 hi, lo;
+        tc::split_tf32(x, hi, lo);
+        const int off = (k & 7) * 16 + c4 * U_SBO + (k >> 3) * U_LBO_A;
+        *reinterpret_cast<float4*>(a_hi + off) = hi;
+        *reinterpret_cast<float4*>(a_lo + off) = lo;
+    }
+    const float* usrc = ubuf + (long)blockIdx.y * (BJ_M * BJ_M);
+#pragma unroll 4
+    for (int i = 0; i < 8; ++i) {
+        const int idx = tid + TC_THREADS * i;
+        const int i4 = idx & 15, k = idx >> 4;
+        const float4 u = *reinterpret_cast<const float4*>(usrc + k * BJ_M + i4 * 4);
+        float4 hi, lo;
+        tc::split_tf32(u, hi, lo);
+        const int off = (k & 7) * 16 + i4 * U_SBO + (k >> 3) * U_LBO_B;
+        *reinterpret_cast<float4*>(b_hi + off) = hi;
+        *reinterpret_cast<float4*>(b_lo + off) = lo;
+    }
+    tc::fence_async_smem();
+    __syncthreads();
+    if (tid == 0) {
+        tc::tc_fence_after();
+        constexpr uint32_t idesc = tc::idesc_tf32(128, 64, 1, 1);
+        const uint32_t ah = tc::smem_u32(a_hi), al = tc::smem_u32(a_lo);
+        const uint32_t bh = tc::smem_u32(b_hi), bl = tc::smem_u32(b_lo);
+#pragma unroll
+        for (int pass = 0; pass < 3; ++pass) {
+            const uint32_t ab = pass == 1 ? al : ah;
+            const uint32_t bb = pass == 2 ? bl : bh;
+#pragma unroll
+            for (int j = 0; j < BJ_M / 8; ++j) {
+                const uint64_t ad = tc::smem_desc(ab + j * U_LBO_A, U_LBO_A, U_SBO);
+                const uint64_t bd = tc::smem_desc(bb + j * U_LBO_B, U_LBO_B, U_SBO);
+                tc::umma_tf32(tmem, ad, bd, idesc, !(pass == 0 && j == 0));
+            }
+        }
+        tc::umma_commit(&mbar);
+    }
+    tc::mbar_wait(&mbar, 0);
+    tc::tc_fence_after();
+    // D[c][i]: TMEM lane = c (this thread: c = 32*warp + lane), column = i
+    float v[32];
+    const uint32_t taddr = tmem + ((uint32_t)(32 * warp) << 16);
+    const int c = c0 + 32 * warp + lane;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        tc::tmem_ld32(taddr + 32 * h, v);
+        if (c < ld) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+                const int r = 32 * h + i;
+                const int grow = (r < BJ_B) ? bi * BJ_B + r : bj * BJ_B + (r - BJ_B);
+                mt.X[(long)grow * ld + c] = v[i];
+            }
+        }
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tc::tmem_dealloc<64>(tmem);
 }
 
 // inner eigenproblem: sum the Gram partials, Jacobi in shared memory, emit U.  grid total_pairs
@@ -317,15 +534,20 @@ bj_solve_kernel(const BjMat* mats, const int* pair_mat, BjState* state, int roun
     const float* src = partial + partial_off[mi] +
                        (long)(blockIdx.x - mt.pair_begin) * mt.ksplit * (BJ_M * BJ_M);
     for (int e = tid; e < BJ_M * BJ_M; e += blockDim.x) {
-        float s = 0.f;
-        for (int z = 0; z < mt.ksplit; ++z) s += src[(long)z * (BJ_M * BJ_M) + e];
         const int i = e / BJ_M, j = e - i * BJ_M;
-        S[i * P + j] = s;
+        const int et = j * BJ_M + i;                 // H is symmetric only up to rounding: use (H + H^T)/2
+        float s = 0.f;
+        for (int z = 0; z < mt.ksplit; ++z)
+            s += src[(long)z * (BJ_M * BJ_M) + e] + src[(long)z * (BJ_M * BJ_M) + et];
+        S[i * P + j] = 0.5f * s;
         U[i * P + j] = (i == j) ? 1.f : 0.f;
     }
     __syncthreads();
     int sig = 0;
-    jacobi_smem<BJ_M>(S, U, BJ_M, P, 1.0e-7f, 1e-36f, mt.tol_conv, inner_sweeps, &sig);
+    const float scale = __int_as_float(state[mi].scale_bits);
+    // rotate while an element is above the fp32 noise floor (relative AND absolute);
+    // "not converged" = some element still above tol_conv * max|diag A|
+    jacobi_smem<BJ_M>(S, U, BJ_M, P, 1.0e-7f, 5e-8f * scale, mt.tol_conv * scale, inner_sweeps, &sig);
     float* dst = ubuf + (long)blockIdx.x * (BJ_M * BJ_M);
     for (int e = tid; e < BJ_M * BJ_M; e += blockDim.x) {
         const int i = e / BJ_M, j = e - i * BJ_M;
@@ -501,6 +723,21 @@ __global__ void bj_store_sweeps_kernel(const BjState* state, const int* out_inde
     if (i < nmat) sweeps_out[out_index[i]] = state[i].sweeps;
 }
 
+// Newton-Schulz re-orthogonalisation of the accumulated eigenvector rows:
+//   E = V V^T - I  (into the W half of X),  V <- V - 0.5 E V  (via the Q buffer)
+struct EpiGramMinusI {
+    float* X; long ld;
+    __device__ __forceinline__ void operator()(int m, int n, float v) const {
+        X[(long)m * ld + n] = v - (m == n ? 1.f : 0.f);
+    }
+};
+struct EpiNsUpdate {
+    float* Q; const float* X; long ld; int n, n_pad;
+    __device__ __forceinline__ void operator()(int m, int c, float v) const {
+        Q[(long)m * n + c] = fmaf(-0.5f, v, X[(long)m * ld + n_pad + c]);
+    }
+};
+
 // epilogue of the Rayleigh GEMM: Y -> W half of X (row stride 2 n_pad)
 struct EpiToX {
     float* X; long ld;
@@ -644,8 +881,7 @@ extern "C" int kfacb_eigh_batched(const int32_t* n, int32_t count,
             b.lam = (float*)(ws + lo); b.nrm = b.lam + b.n_pad; lo += 2 * (size_t)b.n_pad * sizeof(float);
             b.perm = (int*)(ws + po); po += (size_t)b.n_pad * sizeof(int);
             b.pair_begin = pair; b.ksplit = cdiv(b.n_pad, BJ_KCHUNK);
-            const float t = 6e-8f * sqrtf((float)b.n);
-            b.tol_conv = t > 2e-6f ? t : 2e-6f;
+            b.tol_conv = 1e-6f * (float)env_int("KFACB_CONV_TOL_E6", 2);
             hpoff[k] = partial_off;
             partial_off += (long)(b.p / 2) * b.ksplit * BJ_M * BJ_M;
             for (int q = 0; q < b.p / 2; ++q) hpm[pair++] = k;
@@ -671,7 +907,7 @@ extern "C" int kfacb_eigh_batched(const int32_t* n, int32_t count,
     if (!h_active) { set_error("cannot allocate the pinned progress flag"); return KFACB_ERR_CUDA; }
     *h_active = 1;
 
-    bj_init_kernel<<<dim3(4 * sm_count(), nb), 256, 0, st>>>(dm);
+    bj_init_kernel<<<dim3(4 * sm_count(), nb), 256, 0, st>>>(dm, dstate);
     KFACB_CHECK_LAUNCH();
 
     const size_t upd_smem = (size_t)(BJ_M * BJ_M + BJ_M * TILE) * sizeof(float);
@@ -683,15 +919,26 @@ extern "C" int kfacb_eigh_batched(const int32_t* n, int32_t count,
     KFACB_CHECK_CUDA(cudaEventCreateWithFlags(&ev[1], cudaEventDisableTiming));
     int rc = KFACB_OK;
     const int inner_sweeps = env_int("KFACB_INNER_SWEEPS", BJ_INNER_SWEEPS);   // tuning knobs
+    const bool use_tc = env_int("KFACB_JACOBI_SIMT", 0) == 0;                  // 1 = fp32 SIMT GEMMs (debug / A-B)
+    if (use_tc) {
+        KFACB_CHECK_CUDA(cudaFuncSetAttribute(bj_h_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, H_SMEM));
+        KFACB_CHECK_CUDA(cudaFuncSetAttribute(bj_update_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, U_SMEM));
+    }
     const int max_sweeps = env_int("KFACB_MAX_SWEEPS", BJ_MAX_SWEEPS);
     for (int r = 0; r < pl.max_rounds; ++r) {
         if (r % CH == 0 && r >= 2 * CH) {
             if (cudaEventSynchronize(ev[(r / CH) & 1]) != cudaSuccess) { rc = KFACB_ERR_CUDA; set_error("event sync failed"); break; }
             if (*(volatile int*)h_active == 0) break;
         }
-        bj_gram_kernel<<<dim3(pl.total_pairs, pl.max_ksplit), 256, 0, st>>>(dm, dpm, dstate, r, partial, dpoff);
+        if (use_tc)
+            bj_h_tc_kernel<<<dim3(pl.total_pairs, pl.max_ksplit), TC_THREADS, H_SMEM, st>>>(dm, dpm, dstate, r, partial, dpoff);
+        else
+            bj_gram_kernel<<<dim3(pl.total_pairs, pl.max_ksplit), 256, 0, st>>>(dm, dpm, dstate, r, partial, dpoff);
         bj_solve_kernel<<<pl.total_pairs, 256, 0, st>>>(dm, dpm, dstate, r, partial, dpoff, ubuf, inner_sweeps);
-        bj_update_kernel<<<dim3(col_tiles, pl.total_pairs), 256, upd_smem, st>>>(dm, dpm, dstate, r, ubuf);
+        if (use_tc)
+            bj_update_tc_kernel<<<dim3(col_tiles, pl.total_pairs), TC_THREADS, U_SMEM, st>>>(dm, dpm, dstate, r, ubuf);
+        else
+            bj_update_kernel<<<dim3(col_tiles, pl.total_pairs), 256, upd_smem, st>>>(dm, dpm, dstate, r, ubuf);
         bj_check_kernel<<<1, 256, 0, st>>>(dm, dstate, nb, r, max_sweeps, d_active);
         count_launch(4);
         if (cudaGetLastError() != cudaSuccess) { rc = KFACB_ERR_CUDA; set_error("jacobi round launch failed"); break; }
@@ -700,6 +947,20 @@ extern "C" int kfacb_eigh_batched(const int32_t* n, int32_t count,
     cudaEventDestroy(ev[0]); cudaEventDestroy(ev[1]);
     if (rc) return rc;
 
+    // one Newton-Schulz step removes the orthogonality drift of ~1e3 accumulated fp32 rotations
+    if (env_int("KFACB_NS", 1)) {
+        for (int k = 0; k < nb; ++k) {
+            const BjMat& b = hm[k];
+            const long ld = 2L * b.n_pad;
+            LdKContig lv{b.X + b.n_pad, ld, b.n, b.n};
+            KFACB_CHECK_CUDA(launch_gemm(lv, lv, EpiGramMinusI{b.X, ld}, b.n, b.n, b.n, st));
+            LdKContig le{b.X, ld, b.n, b.n};
+            LdMnContig lvt{b.X + b.n_pad, ld, b.n, b.n};
+            KFACB_CHECK_CUDA(launch_gemm(le, lvt, EpiNsUpdate{b.Q, b.X, ld, b.n, b.n_pad}, b.n, b.n, b.n, st));
+            KFACB_CHECK_CUDA(cudaMemcpy2DAsync(b.X + b.n_pad, ld * sizeof(float), b.Q, (size_t)b.n * sizeof(float),
+                                               (size_t)b.n * sizeof(float), b.n, cudaMemcpyDeviceToDevice, st));
+        }
+    }
     // Rayleigh quotients: Y = V^T A  (row i of Y = A v_i), written over the W half
     for (int k = 0; k < nb; ++k) {
         const BjMat& b = hm[k];

@@ -17,12 +17,21 @@ def wishart(n, rows, gen, dev):
     return (0.05 * torch.eye(n, device=dev) + 0.95 * a).contiguous()
 
 
+def graded(n, gen, dev):
+    q, _ = torch.linalg.qr(torch.randn(n, n, device=dev, generator=gen, dtype=torch.float64))
+    m = (q * torch.logspace(-8, 0, n, device=dev, dtype=torch.float64)) @ q.t()
+    return (0.5 * (m + m.t())).float().contiguous()
+
+
 def main():
     dev = torch.device('cuda:0')
     eng = NativeEngine(dev)
     ns = [int(x) for x in sys.argv[1:]] or [4608]
     gen = torch.Generator(device=dev).manual_seed(0)
-    mats = [wishart(n, max(1568, 2 * n) if n < 4608 else 1568, gen, dev) for n in ns]
+    if os.environ.get('PROBE_GRADED'):
+        mats = [graded(n, gen, dev) for n in ns]
+    else:
+        mats = [wishart(n, max(1568, 2 * n) if n < 4608 else 1568, gen, dev) for n in ns]
     Qs = [torch.empty_like(m) for m in mats]
     ds = [torch.empty(m.shape[0], device=dev) for m in mats]
     sw = torch.zeros(len(ns), dtype=torch.int32, device=dev)
@@ -35,8 +44,8 @@ def main():
         e1.record()
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1)
-    out = ['inner=%s max=%s ns=%s ms=%.1f launches=%d sweeps=%s' % (
-        os.environ.get('KFACB_INNER_SWEEPS', 'dflt'), os.environ.get('KFACB_MAX_SWEEPS', 'dflt'), ns, ms,
+    out = ['env=%s ns=%s ms=%.1f launches=%d sweeps=%s' % (
+        {k: v for k, v in os.environ.items() if k.startswith(('KFACB_', 'PROBE_'))}, ns, ms,
         eng.launch_count() - l0, sw.tolist())]
     for m, q, d in zip(mats, Qs, ds):
         n = m.shape[0]
@@ -45,9 +54,11 @@ def main():
             derr = (d.double() - ref).abs().max().item() / ref.abs().max().item()
         else:
             derr = float('nan')
-        orth = (q.t() @ q - torch.eye(n, device=dev)).abs().max().item()
+        e = q.t() @ q - torch.eye(n, device=dev)
+        orth = e.abs().max().item()
+        orth2 = torch.linalg.matrix_norm(e.double(), 2).item() if n <= 2304 else e.norm().item()
         rec = ((q * d) @ q.t() - m).norm().item() / m.norm().item()
-        out.append('  n=%d eig_err=%.2e orth=%.2e recon=%.2e' % (n, derr, orth, rec))
+        out.append('  n=%d eig_err=%.2e orth_max=%.2e orth_2norm=%.2e recon=%.2e' % (n, derr, orth, orth2, rec))
     print('\n'.join(out), flush=True)
 
 
