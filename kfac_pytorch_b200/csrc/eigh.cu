@@ -415,13 +415,15 @@ bj_h_tc_kernel(const BjMat* mats, const int* pair_mat, const BjState* state, int
 }
 
 // update kernel (transposed product): D[c][i] = sum_k X[r_k][c] U[k][i]; M = 128 columns of X,
-// N = 64, K = 64.  Both operands MN-major: (mn, k): (mn&3)*4 + (k&7)*16 + (mn>>2)*SBO + (k>>3)*LBO
-constexpr int U_SBO = 128 + 16;                     // +16 B pad: conflict-free staging stores
-constexpr int U_LBO_A = (TILE / 4) * U_SBO;         // 4608
-constexpr int U_LBO_B = (BJ_M / 4) * U_SBO;         // 2304
-constexpr int U_PART_A = (BJ_M / 8) * U_LBO_A;      // 36864
-constexpr int U_PART_B = (BJ_M / 8) * U_LBO_B;      // 18432
-constexpr int U_SMEM = 2 * U_PART_A + 2 * U_PART_B; // 110592
+// N = 64, K = 64.  Both operands are staged K-MAJOR (the layout validated by tools/tc_selftest.cu):
+// each thread gathers 4 consecutive k of ONE column (4 coalesced 32-bit loads across the warp)
+// and stores them as one 16-byte unit:  (mn, k): (mn&7)*16 + (mn>>3)*128 + (k>>2)*LBO + (k&3)*4
+constexpr int U_SBO = 128;
+constexpr int U_LBO_A = (TILE / 8) * 128;           // 2048
+constexpr int U_LBO_B = (BJ_M / 8) * 128;           // 1024
+constexpr int U_PART_A = (BJ_M / 4) * U_LBO_A;      // 32768
+constexpr int U_PART_B = (BJ_M / 4) * U_LBO_B;      // 16384
+constexpr int U_SMEM = 2 * U_PART_A + 2 * U_PART_B; // 98304
 
 __global__ void __launch_bounds__(TC_THREADS)
 bj_update_tc_kernel(const BjMat* mats, const int* pair_mat, const BjState* state, int round,
@@ -447,38 +449,48 @@ bj_update_tc_kernel(const BjMat* mats, const int* pair_mat, const BjState* state
     unsigned char* a_lo = dsm + U_PART_A;
     unsigned char* b_hi = dsm + 2 * U_PART_A;
     unsigned char* b_lo = dsm + 2 * U_PART_A + U_PART_B;
-    // X tile: 64 rows x 128 cols
+    const int c = c0 + tid;                          // this thread's column of X (load AND epilogue)
+    const bool c_ok = c < ld;
+    // X tile: column c, 16 k-quads
+    {
+        const int aoff = (tid & 7) * 16 + (tid >> 3) * U_SBO;
 #pragma unroll 4
-    for (int i = 0; i < 16; ++i) {
-        const int idx = tid + TC_THREADS * i;
-        const int c4 = idx & 31, k = idx >> 5;
-        const int grow = (k < BJ_B) ? bi * BJ_B + k : bj * BJ_B + (k - BJ_B);
-        const int c = c0 + c4 * 4;
-        float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (c < ld) x = *reinterpret_cast<const float4*>(mt.X + (long)grow * ld + c);
-        float4 hi, lo;
-        tc::split_tf32(x, hi, lo);
-        const int off = (k & 7) * 16 + c4 * U_SBO + (k >> 3) * U_LBO_A;
-        *reinterpret_cast<float4*>(a_hi + off) = hi;
-        *reinterpret_cast<float4*>(a_lo + off) = lo;
+        for (int kq = 0; kq < BJ_M / 4; ++kq) {
+            float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (c_ok) {
+                const int k = 4 * kq;                // BJ_B is a multiple of 4: a quad never straddles the two blocks
+                const int grow = (k < BJ_B) ? bi * BJ_B + k : bj * BJ_B + (k - BJ_B);
+                const float* src = mt.X + (long)grow * ld + c;
+                x.x = src[0]; x.y = src[ld]; x.z = src[2 * ld]; x.w = src[3 * ld];
+            }
+            float4 hi, lo;
+            tc::split_tf32(x, hi, lo);
+            *reinterpret_cast<float4*>(a_hi + aoff + kq * U_LBO_A) = hi;
+            *reinterpret_cast<float4*>(a_lo + aoff + kq * U_LBO_A) = lo;
+        }
     }
-    const float* usrc = ubuf + (long)blockIdx.y * (BJ_M * BJ_M);
+    // U: column i, k-quads (tid>>6) + 2t
+    {
+        const float* usrc = ubuf + (long)blockIdx.y * (BJ_M * BJ_M);
+        const int i = tid & 63;
+        const int boff = (i & 7) * 16 + (i >> 3) * U_SBO;
 #pragma unroll 4
-    for (int i = 0; i < 8; ++i) {
-        const int idx = tid + TC_THREADS * i;
-        const int i4 = idx & 15, k = idx >> 4;
-        const float4 u = *reinterpret_cast<const float4*>(usrc + k * BJ_M + i4 * 4);
-        float4 hi, lo;
-        tc::split_tf32(u, hi, lo);
-        const int off = (k & 7) * 16 + i4 * U_SBO + (k >> 3) * U_LBO_B;
-        *reinterpret_cast<float4*>(b_hi + off) = hi;
-        *reinterpret_cast<float4*>(b_lo + off) = lo;
+        for (int t = 0; t < BJ_M / 8; ++t) {
+            const int kq = (tid >> 6) + 2 * t;
+            const float* src = usrc + (4 * kq) * BJ_M + i;
+            float4 u;
+            u.x = src[0]; u.y = src[BJ_M]; u.z = src[2 * BJ_M]; u.w = src[3 * BJ_M];
+            float4 hi, lo;
+            tc::split_tf32(u, hi, lo);
+            *reinterpret_cast<float4*>(b_hi + boff + kq * U_LBO_B) = hi;
+            *reinterpret_cast<float4*>(b_lo + boff + kq * U_LBO_B) = lo;
+        }
     }
     tc::fence_async_smem();
     __syncthreads();
     if (tid == 0) {
         tc::tc_fence_after();
-        constexpr uint32_t idesc = tc::idesc_tf32(128, 64, 1, 1);
+        constexpr uint32_t idesc = tc::idesc_tf32(128, 64, 0, 0);
         const uint32_t ah = tc::smem_u32(a_hi), al = tc::smem_u32(a_lo);
         const uint32_t bh = tc::smem_u32(b_hi), bl = tc::smem_u32(b_lo);
 #pragma unroll
@@ -487,8 +499,8 @@ bj_update_tc_kernel(const BjMat* mats, const int* pair_mat, const BjState* state
             const uint32_t bb = pass == 2 ? bl : bh;
 #pragma unroll
             for (int j = 0; j < BJ_M / 8; ++j) {
-                const uint64_t ad = tc::smem_desc(ab + j * U_LBO_A, U_LBO_A, U_SBO);
-                const uint64_t bd = tc::smem_desc(bb + j * U_LBO_B, U_LBO_B, U_SBO);
+                const uint64_t ad = tc::smem_desc(ab + 2 * j * U_LBO_A, U_LBO_A, U_SBO);
+                const uint64_t bd = tc::smem_desc(bb + 2 * j * U_LBO_B, U_LBO_B, U_SBO);
                 tc::umma_tf32(tmem, ad, bd, idesc, !(pass == 0 && j == 0));
             }
         }
@@ -499,11 +511,11 @@ bj_update_tc_kernel(const BjMat* mats, const int* pair_mat, const BjState* state
     // D[c][i]: TMEM lane = c (this thread: c = 32*warp + lane), column = i
     float v[32];
     const uint32_t taddr = tmem + ((uint32_t)(32 * warp) << 16);
-    const int c = c0 + 32 * warp + lane;
+    (void)lane;
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
         tc::tmem_ld32(taddr + 32 * h, v);
-        if (c < ld) {
+        if (c_ok) {
 #pragma unroll
             for (int i = 0; i < 32; ++i) {
                 const int r = 32 * h + i;
