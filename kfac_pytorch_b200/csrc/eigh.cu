@@ -28,7 +28,7 @@ constexpr int BJ_B = 32;              // rows per block
 constexpr int BJ_M = 2 * BJ_B;        // rows per pair = size of the inner eigenproblem
 constexpr int BJ_KCHUNK = 256;        // Gram split-K chunk
 constexpr int BJ_MAX_SWEEPS = 16;
-constexpr int BJ_INNER_SWEEPS = 10;   // cap of Jacobi sweeps on the 64x64 Gram per visit
+constexpr int BJ_INNER_SWEEPS = 1;    // cap of Jacobi sweeps on the 64x64 Gram per visit
 constexpr int DIRECT_MAX_N = 128;
 
 struct BjMat {
@@ -43,14 +43,16 @@ struct BjMat {
     int nblk;             // real number of blocks
     int pair_begin;       // first global pair index of this matrix
     int ksplit;           // Gram split-K factor
-    float tol_conv;       // |h_pq| / max|diag A| that still counts as "not converged"
+    float tol_conv;       // sweep-time off-norm / ||A||_F below which the matrix is converged
 };
 
 struct BjState {          // per matrix, device
     int scale_bits;       // float bits of max |diag(A)| (absolute scale for the thresholds)
     int converged;
-    int rot;              // significant rotations in the current sweep
+    int rot;              // unused (kept for layout stability)
     int sweeps;
+    float off2;           // sum over the pairs visited this sweep of ||cross block of H||_F^2
+    float norm2;          // ||A||_F^2
 };
 
 // ---------------------------------------------------------------------------
@@ -237,16 +239,19 @@ __global__ void bj_init_kernel(const BjMat* mats, BjState* state) {
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < mt.n; i += gridDim.x * blockDim.x)
         dmax = fmaxf(dmax, fabsf(mt.A[(long)i * mt.n + i]));
     if (dmax > 0.f) atomicMax(&state[blockIdx.y].scale_bits, __float_as_int(dmax));
+    float ss = 0.f;
     const long ld = 2L * mt.n_pad;
     const long tot = (long)mt.n_pad * ld;
     for (long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < tot;
          e += (long)gridDim.x * blockDim.x) {
         const int i = (int)(e / ld), c = (int)(e - (long)i * ld);
         float v;
-        if (c < mt.n_pad) v = (i < mt.n && c < mt.n) ? 0.5f * (mt.A[(long)i * mt.n + c] + mt.A[(long)c * mt.n + i]) : 0.f;
+        if (c < mt.n_pad) { v = (i < mt.n && c < mt.n) ? 0.5f * (mt.A[(long)i * mt.n + c] + mt.A[(long)c * mt.n + i]) : 0.f; ss = fmaf(v, v, ss); }
         else v = (c - mt.n_pad == i) ? 1.f : 0.f;
         mt.X[e] = v;
     }
+    ss = warp_sum(ss);
+    if ((threadIdx.x & 31) == 0 && ss > 0.f) atomicAdd(&state[blockIdx.y].norm2, ss);
 }
 
 // Projected block H = V_R^T A V_R = V_R W_R^T (64x64) of one pair over one k-chunk (SIMT
@@ -425,22 +430,26 @@ constexpr int U_PART_A = (BJ_M / 4) * U_LBO_A;      // 32768
 constexpr int U_PART_B = (BJ_M / 4) * U_LBO_B;      // 16384
 constexpr int U_SMEM = 2 * U_PART_A + 2 * U_PART_B; // 98304
 
+// One CTA owns `tiles_per_cta` consecutive 128-column tiles of one pair: U is staged once, the
+// X loads of tile t+1 are in flight while the tensor core works on tile t and the epilogue of
+// tile t-1 drains the other TMEM accumulator (2 x 64 columns, double buffered).
 __global__ void __launch_bounds__(TC_THREADS)
 bj_update_tc_kernel(const BjMat* mats, const int* pair_mat, const BjState* state, int round,
-                    const float* __restrict__ ubuf) {
+                    const float* __restrict__ ubuf, int tiles_per_cta) {
     extern __shared__ __align__(128) unsigned char dsm[];
-    __shared__ __align__(8) uint64_t mbar;
+    __shared__ __align__(8) uint64_t mbar[2];
     __shared__ uint32_t tmem_slot;
     const int mi = pair_mat[blockIdx.y];
     const BjMat mt = mats[mi];
     const long ld = 2L * mt.n_pad;
-    const int c0 = blockIdx.x * TILE;
-    if (state[mi].converged || c0 >= ld) return;
+    const int tile0 = blockIdx.x * tiles_per_cta;
+    if (state[mi].converged || (long)tile0 * TILE >= ld) return;
     int bi, bj;
     if (!bj_pair_blocks(mt, blockIdx.y - mt.pair_begin, round, bi, bj)) return;
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    if (tid == 0) { tc::mbar_init(&mbar, 1); tc::fence_mbar_init(); }
-    if (warp == 0) tc::tmem_alloc<64>(&tmem_slot);
+    const int ntiles = min(tiles_per_cta, (int)((ld - (long)tile0 * TILE + TILE - 1) / TILE));
+    const int tid = threadIdx.x, warp = tid >> 5;
+    if (tid == 0) { tc::mbar_init(&mbar[0], 1); tc::mbar_init(&mbar[1], 1); tc::fence_mbar_init(); }
+    if (warp == 0) tc::tmem_alloc<128>(&tmem_slot);
     tc::tc_fence_before();
     __syncthreads();
     tc::tc_fence_after();
@@ -449,32 +458,34 @@ bj_update_tc_kernel(const BjMat* mats, const int* pair_mat, const BjState* state
     unsigned char* a_lo = dsm + U_PART_A;
     unsigned char* b_hi = dsm + 2 * U_PART_A;
     unsigned char* b_lo = dsm + 2 * U_PART_A + U_PART_B;
-    const int c = c0 + tid;                          // this thread's column of X (load AND epilogue)
-    const bool c_ok = c < ld;
-    // X tile: column c, 16 k-quads
-    {
-        const int aoff = (tid & 7) * 16 + (tid >> 3) * U_SBO;
-#pragma unroll 4
-        for (int kq = 0; kq < BJ_M / 4; ++kq) {
-            float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (c_ok) {
-                const int k = 4 * kq;                // BJ_B is a multiple of 4: a quad never straddles the two blocks
-                const int grow = (k < BJ_B) ? bi * BJ_B + k : bj * BJ_B + (k - BJ_B);
-                const float* src = mt.X + (long)grow * ld + c;
-                x.x = src[0]; x.y = src[ld]; x.z = src[2 * ld]; x.w = src[3 * ld];
-            }
-            float4 hi, lo;
-            tc::split_tf32(x, hi, lo);
-            *reinterpret_cast<float4*>(a_hi + aoff + kq * U_LBO_A) = hi;
-            *reinterpret_cast<float4*>(a_lo + aoff + kq * U_LBO_A) = lo;
-        }
+    const float* rowp[BJ_M / 4];                     // first row of each k-quad (a quad never straddles the 2 blocks)
+#pragma unroll
+    for (int kq = 0; kq < BJ_M / 4; ++kq) {
+        const int k = 4 * kq;
+        const int grow = (k < BJ_B) ? bi * BJ_B + k : bj * BJ_B + (k - BJ_B);
+        rowp[kq] = mt.X + (long)grow * ld;
     }
+    float x[BJ_M];
+    auto load_tile = [&](int t) {
+        const long c = (long)(tile0 + t) * TILE + tid;
+        if (c < ld) {
+#pragma unroll
+            for (int kq = 0; kq < BJ_M / 4; ++kq) {
+                const float* src = rowp[kq] + c;
+                x[4 * kq] = src[0]; x[4 * kq + 1] = src[ld]; x[4 * kq + 2] = src[2 * ld]; x[4 * kq + 3] = src[3 * ld];
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < BJ_M; ++k) x[k] = 0.f;
+        }
+    };
+    load_tile(0);
     // U: column i, k-quads (tid>>6) + 2t
     {
         const float* usrc = ubuf + (long)blockIdx.y * (BJ_M * BJ_M);
         const int i = tid & 63;
         const int boff = (i & 7) * 16 + (i >> 3) * U_SBO;
-#pragma unroll 4
+#pragma unroll
         for (int t = 0; t < BJ_M / 8; ++t) {
             const int kq = (tid >> 6) + 2 * t;
             const float* src = usrc + (4 * kq) * BJ_M + i;
@@ -486,57 +497,81 @@ bj_update_tc_kernel(const BjMat* mats, const int* pair_mat, const BjState* state
             *reinterpret_cast<float4*>(b_lo + boff + kq * U_LBO_B) = lo;
         }
     }
-    tc::fence_async_smem();
-    __syncthreads();
-    if (tid == 0) {
-        tc::tc_fence_after();
-        constexpr uint32_t idesc = tc::idesc_tf32(128, 64, 0, 0);
-        const uint32_t ah = tc::smem_u32(a_hi), al = tc::smem_u32(a_lo);
-        const uint32_t bh = tc::smem_u32(b_hi), bl = tc::smem_u32(b_lo);
+    const int aoff = (tid & 7) * 16 + (tid >> 3) * U_SBO;
+    auto epilogue = [&](int t) {                     // D[c][i]: TMEM lane = c (this thread), column = i
+        const long c = (long)(tile0 + t) * TILE + tid;
+        const uint32_t taddr = tmem + ((uint32_t)(32 * warp) << 16) + 64 * (t & 1);
+        float v[32];
 #pragma unroll
-        for (int pass = 0; pass < 3; ++pass) {
-            const uint32_t ab = pass == 1 ? al : ah;
-            const uint32_t bb = pass == 2 ? bl : bh;
+        for (int h = 0; h < 2; ++h) {
+            tc::tmem_ld32(taddr + 32 * h, v);
+            if (c < ld) {
 #pragma unroll
-            for (int j = 0; j < BJ_M / 8; ++j) {
-                const uint64_t ad = tc::smem_desc(ab + 2 * j * U_LBO_A, U_LBO_A, U_SBO);
-                const uint64_t bd = tc::smem_desc(bb + 2 * j * U_LBO_B, U_LBO_B, U_SBO);
-                tc::umma_tf32(tmem, ad, bd, idesc, !(pass == 0 && j == 0));
+                for (int i = 0; i < 32; ++i) {
+                    const int r = 32 * h + i;
+                    const int grow = (r < BJ_B) ? bi * BJ_B + r : bj * BJ_B + (r - BJ_B);
+                    mt.X[(long)grow * ld + c] = v[i];
+                }
             }
         }
-        tc::umma_commit(&mbar);
+    };
+    for (int t = 0; t < ntiles; ++t) {
+        if (t > 0) tc::mbar_wait(&mbar[(t - 1) & 1], (uint32_t)(((t - 1) >> 1) & 1));   // MMA(t-1) done: smem A free, D(t-1) ready
+#pragma unroll
+        for (int kq = 0; kq < BJ_M / 4; ++kq) {
+            float4 hi, lo;
+            tc::split_tf32(make_float4(x[4 * kq], x[4 * kq + 1], x[4 * kq + 2], x[4 * kq + 3]), hi, lo);
+            *reinterpret_cast<float4*>(a_hi + aoff + kq * U_LBO_A) = hi;
+            *reinterpret_cast<float4*>(a_lo + aoff + kq * U_LBO_A) = lo;
+        }
+        tc::fence_async_smem();
+        tc::tc_fence_before();
+        __syncthreads();
+        if (tid == 0) {
+            tc::tc_fence_after();
+            constexpr uint32_t idesc = tc::idesc_tf32(128, 64, 0, 0);
+            const uint32_t ah = tc::smem_u32(a_hi), al = tc::smem_u32(a_lo);
+            const uint32_t bh = tc::smem_u32(b_hi), bl = tc::smem_u32(b_lo);
+            const uint32_t d = tmem + 64 * (t & 1);
+#pragma unroll
+            for (int pass = 0; pass < 3; ++pass) {
+                const uint32_t ab = pass == 1 ? al : ah;
+                const uint32_t bb = pass == 2 ? bl : bh;
+#pragma unroll
+                for (int j = 0; j < BJ_M / 8; ++j) {
+                    const uint64_t ad = tc::smem_desc(ab + 2 * j * U_LBO_A, U_LBO_A, U_SBO);
+                    const uint64_t bd = tc::smem_desc(bb + 2 * j * U_LBO_B, U_LBO_B, U_SBO);
+                    tc::umma_tf32(d, ad, bd, idesc, !(pass == 0 && j == 0));
+                }
+            }
+            tc::umma_commit(&mbar[t & 1]);
+        }
+        if (t + 1 < ntiles) load_tile(t + 1);
+        if (t > 0) { tc::tc_fence_after(); epilogue(t - 1); }
     }
-    tc::mbar_wait(&mbar, 0);
+    tc::mbar_wait(&mbar[(ntiles - 1) & 1], (uint32_t)(((ntiles - 1) >> 1) & 1));
     tc::tc_fence_after();
-    // D[c][i]: TMEM lane = c (this thread: c = 32*warp + lane), column = i
-    float v[32];
-    const uint32_t taddr = tmem + ((uint32_t)(32 * warp) << 16);
-    (void)lane;
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-        tc::tmem_ld32(taddr + 32 * h, v);
-        if (c_ok) {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) {
-                const int r = 32 * h + i;
-                const int grow = (r < BJ_B) ? bi * BJ_B + r : bj * BJ_B + (r - BJ_B);
-                mt.X[(long)grow * ld + c] = v[i];
-            }
-        }
-    }
+    epilogue(ntiles - 1);
     tc::tc_fence_before();
     __syncthreads();
-    if (warp == 0) tc::tmem_dealloc<64>(tmem);
+    if (warp == 0) tc::tmem_dealloc<128>(tmem);
 }
 
-// inner eigenproblem: sum the Gram partials, Jacobi in shared memory, emit U.  grid total_pairs
-__global__ void __launch_bounds__(256)
+// inner eigenproblem: sum the H partials (symmetrised), cyclic two-sided Jacobi sweeps on the
+// 64x64 block in shared memory, emit the accumulated rotations U.  grid total_pairs, 512 threads.
+// Fully unrolled, branch-free rotation application (skipped pairs carry c = 1, s = 0), one
+// float4 {c, s, p, q} per pair: ~1k cycles per round instead of ~7k for the generic routine.
+constexpr int SOLVE_THREADS = 512;
+__global__ void __launch_bounds__(SOLVE_THREADS)
 bj_solve_kernel(const BjMat* mats, const int* pair_mat, BjState* state, int round,
                 const float* __restrict__ partial, const long* partial_off,
                 float* __restrict__ ubuf, int inner_sweeps) {
-    constexpr int P = BJ_M + 1;
-    __shared__ float S[BJ_M * P];
-    __shared__ float U[BJ_M * P];
+    constexpr int M = BJ_M, P = BJ_M + 1, HALF = BJ_M / 2, MM1 = BJ_M - 1;
+    constexpr int PPT = HALF / (SOLVE_THREADS / M);          // pairs per thread per phase (4)
+    __shared__ float S[M * P];
+    __shared__ float U[M * P];
+    __shared__ float4 rot[HALF];
+    __shared__ float red[SOLVE_THREADS / 32];
     const int mi = pair_mat[blockIdx.x];
     const BjMat mt = mats[mi];
     if (state[mi].converged) return;
@@ -544,28 +579,108 @@ bj_solve_kernel(const BjMat* mats, const int* pair_mat, BjState* state, int roun
     if (!bj_pair_blocks(mt, blockIdx.x - mt.pair_begin, round, bi, bj)) return;
     const int tid = threadIdx.x;
     const float* src = partial + partial_off[mi] +
-                       (long)(blockIdx.x - mt.pair_begin) * mt.ksplit * (BJ_M * BJ_M);
-    for (int e = tid; e < BJ_M * BJ_M; e += blockDim.x) {
-        const int i = e / BJ_M, j = e - i * BJ_M;
-        const int et = j * BJ_M + i;                 // H is symmetric only up to rounding: use (H + H^T)/2
-        float s = 0.f;
+                       (long)(blockIdx.x - mt.pair_begin) * mt.ksplit * (M * M);
+    float off2 = 0.f;
+    for (int e = tid; e < M * M; e += SOLVE_THREADS) {
+        const int i = e / M, j = e - i * M;
+        const int et = j * M + i;                    // H is symmetric only up to rounding: use (H + H^T)/2
+        float v = 0.f;
         for (int z = 0; z < mt.ksplit; ++z)
-            s += src[(long)z * (BJ_M * BJ_M) + e] + src[(long)z * (BJ_M * BJ_M) + et];
-        S[i * P + j] = 0.5f * s;
+            v += src[(long)z * (M * M) + e] + src[(long)z * (M * M) + et];
+        v *= 0.5f;
+        S[i * P + j] = v;
         U[i * P + j] = (i == j) ? 1.f : 0.f;
+        if (i < BJ_B && j >= BJ_B) off2 = fmaf(v, v, off2);     // cross block (counted once)
     }
+    off2 = warp_sum(off2);
+    if ((tid & 31) == 0) red[tid >> 5] = off2;
     __syncthreads();
-    int sig = 0;
-    const float scale = __int_as_float(state[mi].scale_bits);
-    // rotate while an element is above the fp32 noise floor (relative AND absolute);
-    // "not converged" = some element still above tol_conv * max|diag A|
-    jacobi_smem<BJ_M>(S, U, BJ_M, P, 1.0e-7f, 5e-8f * scale, mt.tol_conv * scale, inner_sweeps, &sig);
-    float* dst = ubuf + (long)blockIdx.x * (BJ_M * BJ_M);
-    for (int e = tid; e < BJ_M * BJ_M; e += blockDim.x) {
-        const int i = e / BJ_M, j = e - i * BJ_M;
+    if (tid == 0) {
+        float t = 0.f;
+        for (int i = 0; i < SOLVE_THREADS / 32; ++i) t += red[i];
+        if (t > 0.f) atomicAdd(&state[mi].off2, 2.f * t);
+    }
+    const float abs_thr = 5e-8f * __int_as_float(state[mi].scale_bits);
+    const int row = tid & (M - 1), grp = tid >> 6;            // grp in [0, 8)
+    for (int sw = 0; sw < inner_sweeps; ++sw) {
+        int any = 0;
+        for (int r = 0; r < MM1; ++r) {
+            if (tid < HALF) {
+                int p, q;
+                if (tid == 0) { p = MM1; q = r; }
+                else { p = r + tid; if (p >= MM1) p -= MM1; q = r - tid; if (q < 0) q += MM1; }
+                if (p > q) { const int t = p; p = q; q = t; }
+                const float app = S[p * P + p], aqq = S[q * P + q], apq = S[p * P + q];
+                float c = 1.f, sn = 0.f;
+                const float mag = fabsf(apq);
+                if (mag > 1.0e-7f * sqrtf(fabsf(app) * fabsf(aqq)) && mag > abs_thr) {
+                    // angle from fast divide / sqrt (an angle error only leaves a residual a_pq);
+                    // (c, s) is then re-normalised so that c^2 + s^2 = 1 to fp32 rounding.
+                    const float tau = __fdividef(aqq - app, 2.f * apq);
+                    const float t = __fdividef(tau >= 0.f ? 1.f : -1.f, fabsf(tau) + __fsqrt_rn(fmaf(tau, tau, 1.f)));
+                    c = rsqrtf(fmaf(t, t, 1.f));
+                    sn = t * c;
+                    const float f = fmaf(-0.5f, fmaf(c, c, sn * sn), 1.5f);
+                    c *= f; sn *= f;
+                    any = 1;
+                }
+                rot[tid] = make_float4(c, sn, __int_as_float(p), __int_as_float(q));
+            }
+            __syncthreads();
+            // column rotations: S <- S J, U <- U J   (this thread: row `row`, pairs grp, grp+8, ...)
+            {
+                float4 rp[PPT];
+                float sp[PPT], sq[PPT], up[PPT], uq[PPT];
+#pragma unroll
+                for (int u = 0; u < PPT; ++u) rp[u] = rot[grp + 8 * u];
+#pragma unroll
+                for (int u = 0; u < PPT; ++u) {
+                    const int p = __float_as_int(rp[u].z), q = __float_as_int(rp[u].w);
+                    sp[u] = S[row * P + p]; sq[u] = S[row * P + q];
+                    up[u] = U[row * P + p]; uq[u] = U[row * P + q];
+                }
+#pragma unroll
+                for (int u = 0; u < PPT; ++u) {
+                    const int p = __float_as_int(rp[u].z), q = __float_as_int(rp[u].w);
+                    const float c = rp[u].x, sn = rp[u].y;
+                    S[row * P + p] = c * sp[u] - sn * sq[u];
+                    S[row * P + q] = sn * sp[u] + c * sq[u];
+                    U[row * P + p] = c * up[u] - sn * uq[u];
+                    U[row * P + q] = sn * up[u] + c * uq[u];
+                }
+            }
+            __syncthreads();
+            // row rotations: S <- J^T S   (this thread: column `row`); the rotated pair element is set to 0
+            {
+                float4 rp[PPT];
+                float sp[PPT], sq[PPT];
+#pragma unroll
+                for (int u = 0; u < PPT; ++u) rp[u] = rot[grp + 8 * u];
+#pragma unroll
+                for (int u = 0; u < PPT; ++u) {
+                    const int p = __float_as_int(rp[u].z), q = __float_as_int(rp[u].w);
+                    sp[u] = S[p * P + row]; sq[u] = S[q * P + row];
+                }
+#pragma unroll
+                for (int u = 0; u < PPT; ++u) {
+                    const int p = __float_as_int(rp[u].z), q = __float_as_int(rp[u].w);
+                    const float c = rp[u].x, sn = rp[u].y;
+                    float np = c * sp[u] - sn * sq[u];
+                    float nq = sn * sp[u] + c * sq[u];
+                    if (sn != 0.f) { if (row == q) np = 0.f; if (row == p) nq = 0.f; }
+                    S[p * P + row] = np;
+                    S[q * P + row] = nq;
+                }
+            }
+            __syncthreads();
+        }
+        if (!__syncthreads_or(any)) break;
+    }
+    float* dst = ubuf + (long)blockIdx.x * (M * M);
+    for (int e = tid; e < M * M; e += SOLVE_THREADS) {
+        const int i = e / M, j = e - i * M;
         dst[e] = U[i * P + j];
     }
-    if (tid == 0 && sig) atomicAdd(&state[mi].rot, 1);
 }
 
 // rows <- U^T rows for the 64 rows of a pair, 128 columns per CTA.  grid (max col tiles, total_pairs)
@@ -638,8 +753,11 @@ __global__ void bj_check_kernel(const BjMat* mats, BjState* state, int nmat, int
             const int pm1 = mats[mi].p - 1;
             if ((round + 1) % pm1 == 0) {
                 st.sweeps += 1;
-                if (st.rot == 0 || st.sweeps >= max_sweeps) st.converged = 1;
-                st.rot = 0;
+                // off-block-diagonal norm seen DURING this sweep; Jacobi converges quadratically, so once
+                // it is below tol * ||A||_F the sweep just finished has pushed it to fp32 noise level.
+                const float tol = mats[mi].tol_conv;
+                if (st.off2 <= tol * tol * st.norm2 || st.sweeps >= max_sweeps) st.converged = 1;
+                st.off2 = 0.f;
                 state[mi] = st;
             }
             if (!st.converged) atomicAdd(&active, 1);
@@ -893,7 +1011,7 @@ extern "C" int kfacb_eigh_batched(const int32_t* n, int32_t count,
             b.lam = (float*)(ws + lo); b.nrm = b.lam + b.n_pad; lo += 2 * (size_t)b.n_pad * sizeof(float);
             b.perm = (int*)(ws + po); po += (size_t)b.n_pad * sizeof(int);
             b.pair_begin = pair; b.ksplit = cdiv(b.n_pad, BJ_KCHUNK);
-            b.tol_conv = 1e-6f * (float)env_int("KFACB_CONV_TOL_E6", 2);
+            b.tol_conv = 1e-6f * (float)env_int("KFACB_CONV_TOL_E6", 100);
             hpoff[k] = partial_off;
             partial_off += (long)(b.p / 2) * b.ksplit * BJ_M * BJ_M;
             for (int q = 0; q < b.p / 2; ++q) hpm[pair++] = k;
@@ -932,6 +1050,7 @@ extern "C" int kfacb_eigh_batched(const int32_t* n, int32_t count,
     int rc = KFACB_OK;
     const int inner_sweeps = env_int("KFACB_INNER_SWEEPS", BJ_INNER_SWEEPS);   // tuning knobs
     const bool use_tc = env_int("KFACB_JACOBI_SIMT", 0) == 0;                  // 1 = fp32 SIMT GEMMs (debug / A-B)
+    const int upd_g = max(1, env_int("KFACB_UPD_TILES", 4));                   // 128-column tiles per update CTA
     if (use_tc) {
         KFACB_CHECK_CUDA(cudaFuncSetAttribute(bj_h_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, H_SMEM));
         KFACB_CHECK_CUDA(cudaFuncSetAttribute(bj_update_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, U_SMEM));
@@ -946,9 +1065,9 @@ extern "C" int kfacb_eigh_batched(const int32_t* n, int32_t count,
             bj_h_tc_kernel<<<dim3(pl.total_pairs, pl.max_ksplit), TC_THREADS, H_SMEM, st>>>(dm, dpm, dstate, r, partial, dpoff);
         else
             bj_gram_kernel<<<dim3(pl.total_pairs, pl.max_ksplit), 256, 0, st>>>(dm, dpm, dstate, r, partial, dpoff);
-        bj_solve_kernel<<<pl.total_pairs, 256, 0, st>>>(dm, dpm, dstate, r, partial, dpoff, ubuf, inner_sweeps);
+        bj_solve_kernel<<<pl.total_pairs, SOLVE_THREADS, 0, st>>>(dm, dpm, dstate, r, partial, dpoff, ubuf, inner_sweeps);
         if (use_tc)
-            bj_update_tc_kernel<<<dim3(col_tiles, pl.total_pairs), TC_THREADS, U_SMEM, st>>>(dm, dpm, dstate, r, ubuf);
+            bj_update_tc_kernel<<<dim3(cdiv(col_tiles, upd_g), pl.total_pairs), TC_THREADS, U_SMEM, st>>>(dm, dpm, dstate, r, ubuf, upd_g);
         else
             bj_update_kernel<<<dim3(col_tiles, pl.total_pairs), 256, upd_smem, st>>>(dm, dpm, dstate, r, ubuf);
         bj_check_kernel<<<1, 256, 0, st>>>(dm, dstate, nb, r, max_sweeps, d_active);
