@@ -350,33 +350,41 @@ bj_h_tc_kernel(const BjMat* mats, const int* pair_mat, const BjState* state, int
     const int kbeg = blockIdx.y * BJ_KCHUNK, kend = min(mt.n_pad, kbeg + BJ_KCHUNK);
     const int nslab = (kend - kbeg + H_SLAB - 1) / H_SLAB;
     constexpr uint32_t idesc = tc::idesc_tf32(64, 64, 0, 0);
-    for (int s = 0; s < nslab; ++s) {
+    float4 va[8], wa[8];
+    const float* rbase[8];
+    int soff[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int idx = tid + TC_THREADS * i;
+        const int kq = idx & 15, r = idx >> 4;
+        const int grow = (r < BJ_B) ? bi * BJ_B + r : bj * BJ_B + (r - BJ_B);
+        rbase[i] = mt.X + (long)grow * ld + kq * 4;
+        soff[i] = (r & 7) * 16 + (r >> 3) * H_SBO + kq * H_LBO;
+    }
+    auto load_slab = [&](int s) {
         const int k0 = kbeg + s * H_SLAB;
-        float4 va[8], wa[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-            const int idx = tid + TC_THREADS * i;
-            const int kq = idx & 15, r = idx >> 4;
-            const int grow = (r < BJ_B) ? bi * BJ_B + r : bj * BJ_B + (r - BJ_B);
-            const float* base = mt.X + (long)grow * ld + k0 + kq * 4;
+            const int kq = (tid + TC_THREADS * i) & 15;
             const bool ok = k0 + kq * 4 < kend;
-            wa[i] = ok ? *reinterpret_cast<const float4*>(base) : make_float4(0.f, 0.f, 0.f, 0.f);
-            va[i] = ok ? *reinterpret_cast<const float4*>(base + mt.n_pad) : make_float4(0.f, 0.f, 0.f, 0.f);
+            wa[i] = ok ? *reinterpret_cast<const float4*>(rbase[i] + k0) : make_float4(0.f, 0.f, 0.f, 0.f);
+            va[i] = ok ? *reinterpret_cast<const float4*>(rbase[i] + k0 + mt.n_pad) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
+    };
+    load_slab(0);
+    for (int s = 0; s < nslab; ++s) {
         if (s > 0) tc::mbar_wait(&mbar, (uint32_t)((s - 1) & 1));   // MMAs of the previous slab done reading smem
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-            const int idx = tid + TC_THREADS * i;
-            const int kq = idx & 15, r = idx >> 4;
-            const int off = (r & 7) * 16 + (r >> 3) * H_SBO + kq * H_LBO;
             float4 hi, lo;
             tc::split_tf32(va[i], hi, lo);
-            *reinterpret_cast<float4*>(a_hi + off) = hi;
-            *reinterpret_cast<float4*>(a_lo + off) = lo;
+            *reinterpret_cast<float4*>(a_hi + soff[i]) = hi;
+            *reinterpret_cast<float4*>(a_lo + soff[i]) = lo;
             tc::split_tf32(wa[i], hi, lo);
-            *reinterpret_cast<float4*>(b_hi + off) = hi;
-            *reinterpret_cast<float4*>(b_lo + off) = lo;
+            *reinterpret_cast<float4*>(b_hi + soff[i]) = hi;
+            *reinterpret_cast<float4*>(b_lo + soff[i]) = lo;
         }
+        if (s + 1 < nslab) load_slab(s + 1);        // in flight during the barrier, the MMAs and the next wait
         tc::fence_async_smem();
         __syncthreads();
         if (tid == 0) {
@@ -565,7 +573,7 @@ constexpr int SOLVE_THREADS = 512;
 __global__ void __launch_bounds__(SOLVE_THREADS)
 bj_solve_kernel(const BjMat* mats, const int* pair_mat, BjState* state, int round,
                 const float* __restrict__ partial, const long* partial_off,
-                float* __restrict__ ubuf, int inner_sweeps) {
+                float* __restrict__ ubuf, int inner_sweeps, int full_inner) {
     constexpr int M = BJ_M, P = BJ_M + 1, HALF = BJ_M / 2, MM1 = BJ_M - 1;
     constexpr int PPT = HALF / (SOLVE_THREADS / M);          // pairs per thread per phase (4)
     __shared__ float S[M * P];
@@ -580,17 +588,47 @@ bj_solve_kernel(const BjMat* mats, const int* pair_mat, BjState* state, int roun
     const int tid = threadIdx.x;
     const float* src = partial + partial_off[mi] +
                        (long)(blockIdx.x - mt.pair_begin) * mt.ksplit * (M * M);
+    // sum the split-K partials: float4 loads, 6 independent accumulators in flight (fixed order => deterministic)
+    {
+        const float4* src4 = reinterpret_cast<const float4*>(src);
+#pragma unroll
+        for (int h = 0; h < (M * M / 4) / SOLVE_THREADS; ++h) {
+            const int e4 = tid + h * SOLVE_THREADS;
+            float4 acc[6];
+#pragma unroll
+            for (int u = 0; u < 6; ++u) acc[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            int z = 0;
+            for (; z + 6 <= mt.ksplit; z += 6) {
+#pragma unroll
+                for (int u = 0; u < 6; ++u) {
+                    const float4 t = __ldg(src4 + (long)(z + u) * (M * M / 4) + e4);
+                    acc[u].x += t.x; acc[u].y += t.y; acc[u].z += t.z; acc[u].w += t.w;
+                }
+            }
+            for (; z < mt.ksplit; ++z) {
+                const float4 t = __ldg(src4 + (long)z * (M * M / 4) + e4);
+                acc[0].x += t.x; acc[0].y += t.y; acc[0].z += t.z; acc[0].w += t.w;
+            }
+            const float vx = ((acc[0].x + acc[1].x) + (acc[2].x + acc[3].x)) + (acc[4].x + acc[5].x);
+            const float vy = ((acc[0].y + acc[1].y) + (acc[2].y + acc[3].y)) + (acc[4].y + acc[5].y);
+            const float vz = ((acc[0].z + acc[1].z) + (acc[2].z + acc[3].z)) + (acc[4].z + acc[5].z);
+            const float vw = ((acc[0].w + acc[1].w) + (acc[2].w + acc[3].w)) + (acc[4].w + acc[5].w);
+            const int i = (e4 * 4) / M, j = (e4 * 4) - i * M;
+            U[i * P + j] = vx; U[i * P + j + 1] = vy; U[i * P + j + 2] = vz; U[i * P + j + 3] = vw;   // U = raw H for now
+        }
+    }
+    __syncthreads();
     float off2 = 0.f;
+    for (int e = tid; e < M * M; e += SOLVE_THREADS) {      // H is symmetric only up to rounding: S = (H + H^T)/2
+        const int i = e / M, j = e - i * M;
+        const float v = 0.5f * (U[i * P + j] + U[j * P + i]);
+        S[i * P + j] = v;
+        if (i < BJ_B && j >= BJ_B) off2 = fmaf(v, v, off2);     // cross block (counted once)
+    }
+    __syncthreads();
     for (int e = tid; e < M * M; e += SOLVE_THREADS) {
         const int i = e / M, j = e - i * M;
-        const int et = j * M + i;                    // H is symmetric only up to rounding: use (H + H^T)/2
-        float v = 0.f;
-        for (int z = 0; z < mt.ksplit; ++z)
-            v += src[(long)z * (M * M) + e] + src[(long)z * (M * M) + et];
-        v *= 0.5f;
-        S[i * P + j] = v;
         U[i * P + j] = (i == j) ? 1.f : 0.f;
-        if (i < BJ_B && j >= BJ_B) off2 = fmaf(v, v, off2);     // cross block (counted once)
     }
     off2 = warp_sum(off2);
     if ((tid & 31) == 0) red[tid >> 5] = off2;
@@ -602,14 +640,24 @@ bj_solve_kernel(const BjMat* mats, const int* pair_mat, BjState* state, int roun
     }
     const float abs_thr = 5e-8f * __int_as_float(state[mi].scale_bits);
     const int row = tid & (M - 1), grp = tid >> 6;            // grp in [0, 8)
+    // Element pairs inside one 32-row block meet in EVERY round of the outer sweep, pairs across the
+    // two blocks meet only here.  So: full 63-round tournament at the first round of each outer sweep
+    // (or when full_inner is forced), otherwise just the 32 bipartite rounds {(i, 32 + (i + r) % 32)}.
+    // (with an odd block count one block idles per round: two leading full rounds cover every block)
+    const bool full = full_inner || (round % (mt.p - 1)) < ((mt.nblk & 1) ? 2 : 1);
+    const int nrounds = full ? MM1 : BJ_B;
     for (int sw = 0; sw < inner_sweeps; ++sw) {
         int any = 0;
-        for (int r = 0; r < MM1; ++r) {
+        for (int r = 0; r < nrounds; ++r) {
             if (tid < HALF) {
                 int p, q;
-                if (tid == 0) { p = MM1; q = r; }
-                else { p = r + tid; if (p >= MM1) p -= MM1; q = r - tid; if (q < 0) q += MM1; }
-                if (p > q) { const int t = p; p = q; q = t; }
+                if (full) {
+                    if (tid == 0) { p = MM1; q = r; }
+                    else { p = r + tid; if (p >= MM1) p -= MM1; q = r - tid; if (q < 0) q += MM1; }
+                    if (p > q) { const int t = p; p = q; q = t; }
+                } else {
+                    p = tid; q = BJ_B + ((tid + r) & (BJ_B - 1));
+                }
                 const float app = S[p * P + p], aqq = S[q * P + q], apq = S[p * P + q];
                 float c = 1.f, sn = 0.f;
                 const float mag = fabsf(apq);
@@ -1050,6 +1098,7 @@ extern "C" int kfacb_eigh_batched(const int32_t* n, int32_t count,
     int rc = KFACB_OK;
     const int inner_sweeps = env_int("KFACB_INNER_SWEEPS", BJ_INNER_SWEEPS);   // tuning knobs
     const bool use_tc = env_int("KFACB_JACOBI_SIMT", 0) == 0;                  // 1 = fp32 SIMT GEMMs (debug / A-B)
+    const int full_inner = env_int("KFACB_FULL_INNER", 0);                     // 1 = 63-round inner tournament every visit
     const int upd_g = max(1, env_int("KFACB_UPD_TILES", 4));                   // 128-column tiles per update CTA
     if (use_tc) {
         KFACB_CHECK_CUDA(cudaFuncSetAttribute(bj_h_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, H_SMEM));
@@ -1065,13 +1114,15 @@ extern "C" int kfacb_eigh_batched(const int32_t* n, int32_t count,
             bj_h_tc_kernel<<<dim3(pl.total_pairs, pl.max_ksplit), TC_THREADS, H_SMEM, st>>>(dm, dpm, dstate, r, partial, dpoff);
         else
             bj_gram_kernel<<<dim3(pl.total_pairs, pl.max_ksplit), 256, 0, st>>>(dm, dpm, dstate, r, partial, dpoff);
-        bj_solve_kernel<<<pl.total_pairs, SOLVE_THREADS, 0, st>>>(dm, dpm, dstate, r, partial, dpoff, ubuf, inner_sweeps);
+        bj_solve_kernel<<<pl.total_pairs, SOLVE_THREADS, 0, st>>>(dm, dpm, dstate, r, partial, dpoff, ubuf, inner_sweeps, full_inner);
         if (use_tc)
             bj_update_tc_kernel<<<dim3(cdiv(col_tiles, upd_g), pl.total_pairs), TC_THREADS, U_SMEM, st>>>(dm, dpm, dstate, r, ubuf, upd_g);
         else
             bj_update_kernel<<<dim3(col_tiles, pl.total_pairs), 256, upd_smem, st>>>(dm, dpm, dstate, r, ubuf);
-        bj_check_kernel<<<1, 256, 0, st>>>(dm, dstate, nb, r, max_sweeps, d_active);
-        count_launch(4);
+        bool boundary = false;
+        for (int k = 0; k < nb && !boundary; ++k) boundary = ((r + 1) % (hm[k].p - 1)) == 0;
+        if (boundary) { bj_check_kernel<<<1, 256, 0, st>>>(dm, dstate, nb, r, max_sweeps, d_active); count_launch(1); }
+        count_launch(3);
         if (cudaGetLastError() != cudaSuccess) { rc = KFACB_ERR_CUDA; set_error("jacobi round launch failed"); break; }
         if (r % CH == CH - 1) cudaEventRecord(ev[(r / CH) & 1], st);
     }
