@@ -1,5 +1,6 @@
 // api.cu -- error reporting, device info and other small C-ABI entry points.
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 #include "common.cuh"
 
@@ -16,6 +17,12 @@ void set_error(const char* fmt, ...) {
 
 static unsigned long long g_launches = 0;
 void count_launch(int n) { __atomic_fetch_add(&g_launches, (unsigned long long)n, __ATOMIC_RELAXED); }
+
+bool use_tc_gemm() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("KFACB_GEMM_SIMT"); v = (e && *e && atoi(e) != 0) ? 0 : 1; }
+    return v == 1;
+}
 
 int sm_count() {
     static int cached[64] = {0};

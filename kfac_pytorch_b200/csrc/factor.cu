@@ -11,6 +11,7 @@
 // Tall-skinny problems (rows >> n) are split along the row dimension over
 // gridDim.y with a deterministic second-stage reduction fused with the EMA.
 #include "common.cuh"
+#include "tc_gemm.cuh"
 
 namespace kfacb {
 
@@ -126,6 +127,55 @@ syrk_ema_kernel(L ld, int n, int K, int kchunk, float scale, float alpha, int fi
     }
 }
 
+// tensor-core version of syrk_ema_kernel: same tiling / split-K / epilogue semantics, the 128x128
+// tile product runs on tcgen05 (3xTF32, fp32 accumulation in TMEM) through tcg::mainloop.  Diagonal
+// tiles stage the operand once and use it for both sides.  The drained accumulator is read row-wise
+// for the (m, c) store and column-wise (conflict-free) for the mirrored (c, m) store: both coalesced.
+template <class L>
+__global__ void __launch_bounds__(tcg::THREADS)
+tc_syrk_ema_kernel(L ld, int n, int K, int kchunk, float scale, float alpha, int first_step,
+                   float* __restrict__ factor, float* __restrict__ partial) {
+    extern __shared__ __align__(128) unsigned char dsm_raw[];
+    __shared__ __align__(8) uint64_t mbar;
+    __shared__ uint32_t tmem_slot;
+    tcg::Ctx c;
+    tcg::setup(c, dsm_raw, &mbar, &tmem_slot);
+    const int T = (n + TILE - 1) / TILE;
+    int ti, tj;
+    tri_decode(blockIdx.x, T, ti, tj);
+    const int kbeg = blockIdx.y * kchunk;
+    const int kend = min(K, kbeg + kchunk);
+    tcg::mainloop(ld, ld, ti * TILE, tj * TILE, kbeg, kend, ti == tj, c);
+    const float* d = tcg::drain(c, kend > kbeg);
+    const float keep = 1.f - alpha;
+    const int m0 = ti * TILE, c0 = tj * TILE;
+    if (gridDim.y == 1) {
+        for (int e = threadIdx.x; e < TILE * TILE; e += tcg::THREADS) {
+            const int m = m0 + (e >> 7), cc = c0 + (e & 127);
+            if (m < n && cc < n) {
+                const float old = first_step ? (m == cc ? 1.f : 0.f) : factor[(long)m * n + cc];
+                factor[(long)m * n + cc] = fmaf(alpha, scale * d[(e >> 7) * tcg::DPITCH + (e & 127)], keep * old);
+            }
+        }
+        if (ti != tj) {          // mirrored tile: element (cc, m) takes the value computed for (m, cc)
+            for (int e = threadIdx.x; e < TILE * TILE; e += tcg::THREADS) {
+                const int cc = c0 + (e >> 7), m = m0 + (e & 127);
+                if (m < n && cc < n) {
+                    const float old = first_step ? 0.f : factor[(long)cc * n + m];
+                    factor[(long)cc * n + m] = fmaf(alpha, scale * d[(e & 127) * tcg::DPITCH + (e >> 7)], keep * old);
+                }
+            }
+        }
+    } else {
+        float* dst = partial + (long)blockIdx.y * n * n;
+        for (int e = threadIdx.x; e < TILE * TILE; e += tcg::THREADS) {
+            const int m = m0 + (e >> 7), cc = c0 + (e & 127);
+            if (m < n && cc < n) dst[(long)m * n + cc] = d[(e >> 7) * tcg::DPITCH + (e & 127)];
+        }
+    }
+    tcg::teardown(c);
+}
+
 // second stage of the split-K SYRK: fixed-order sum of the partials + scale + EMA + mirror
 __global__ void syrk_reduce_ema_kernel(const float* __restrict__ partial, int ksplit, int n,
                                        float scale, float alpha, int first_step,
@@ -207,8 +257,18 @@ static int run_syrk(const L& ld, int n, long K, float scale, float alpha, int fi
     const int ksplit = (int)((K + kchunk - 1) / kchunk);
     const int T = cdiv(n, TILE);
     dim3 grid(T * (T + 1) / 2, ksplit);
-    syrk_ema_kernel<L><<<grid, GEMM_THREADS, 0, st>>>(ld, n, (int)K, kchunk, scale, alpha,
-                                                      first_step, factor, partial);
+    if (use_tc_gemm() && K >= 64) {
+        static bool attr_done = false;           // per loader instantiation
+        if (!attr_done) {
+            KFACB_CHECK_CUDA(cudaFuncSetAttribute(tc_syrk_ema_kernel<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, tcg::SMEM));
+            attr_done = true;
+        }
+        tc_syrk_ema_kernel<L><<<grid, tcg::THREADS, tcg::SMEM, st>>>(ld, n, (int)K, kchunk, scale, alpha,
+                                                                   first_step, factor, partial);
+    } else {
+        syrk_ema_kernel<L><<<grid, GEMM_THREADS, 0, st>>>(ld, n, (int)K, kchunk, scale, alpha,
+                                                          first_step, factor, partial);
+    }
     KFACB_CHECK_LAUNCH();
     if (ksplit > 1) {
         const long tot = (long)n * n;

@@ -13,6 +13,7 @@
 // After the last block W = M^-1; it is symmetrised on the way out (the
 // reference's cholesky_inverse result is exactly symmetric).
 #include "common.cuh"
+#include "tc_gemm.cuh"
 
 namespace kfacb {
 
@@ -195,8 +196,8 @@ static int invert_large(const float* M, float* out, int n, float* D, float* C, c
         const int nb = (n - k0 < GJ_NB) ? n - k0 : GJ_NB;
         gj_diag_kernel<<<1, 256, 0, st>>>(out, n, k0, nb, D);
         KFACB_CHECK_LAUNCH();
-        KFACB_CHECK_CUDA(launch_gemm(LdPanel{out, n, k0, nb}, LdDcol{D, nb}, EpiNegStore{C}, n, nb, nb, st));
-        KFACB_CHECK_CUDA(launch_gemm(LdC{C, n, nb}, LdRowBlk{out, n, k0, nb},
+        KFACB_CHECK_CUDA(launch_gemm_auto(LdPanel{out, n, k0, nb}, LdDcol{D, nb}, EpiNegStore{C}, n, nb, nb, st));
+        KFACB_CHECK_CUDA(launch_gemm_auto(LdC{C, n, nb}, LdRowBlk{out, n, k0, nb},
                                      EpiRankUpdate{out, n, k0, nb}, n, n, nb, st));
         gj_fix_kernel<<<cdiv(n, 128), 128, 0, st>>>(out, n, k0, nb, D, C);
         KFACB_CHECK_LAUNCH();

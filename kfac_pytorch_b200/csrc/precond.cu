@@ -4,6 +4,7 @@
 // kfac/kfac_preconditioner_inv_dp.py:126-138 and
 // kfac/kfac_preconditioner_inv.py:145-154,178-217 of the reference.
 #include "common.cuh"
+#include "tc_gemm.cuh"
 
 namespace kfacb {
 
@@ -151,19 +152,19 @@ extern "C" int kfacb_precond_eigen(const kfacb_layer_t* layers, int32_t count,
                       "layer %d: null pointer", i);
         const int dW = nA - (l.has_bias ? 1 : 0);
         // T1 = grad QA
-        KFACB_CHECK_CUDA(launch_gemm(LdGrad{wgrad[i], bgrad[i], nG, dW, nA},
+        KFACB_CHECK_CUDA(launch_gemm_auto(LdGrad{wgrad[i], bgrad[i], nG, dW, nA},
                                      LdMnContig{QA[i], (long)nA, nA, nA},
                                      EpiStore{t0, (long)nA, 1.f, 0.f}, nG, nA, nA, st));
         // V2 = (QG^T T1) / (dG dA^T + damping)
-        KFACB_CHECK_CUDA(launch_gemm(LdMnContig{QG[i], (long)nG, nG, nG},
+        KFACB_CHECK_CUDA(launch_gemm_auto(LdMnContig{QG[i], (long)nG, nG, nG},
                                      LdMnContig{t0, (long)nA, nA, nG},
                                      EpiEigDivide{t1, (long)nA, dG[i], dA[i], damping}, nG, nA, nG, st));
         // T2 = V2 QA^T
-        KFACB_CHECK_CUDA(launch_gemm(LdKContig{t1, (long)nA, nG, nA},
+        KFACB_CHECK_CUDA(launch_gemm_auto(LdKContig{t1, (long)nA, nG, nA},
                                      LdKContig{QA[i], (long)nA, nA, nA},
                                      EpiStore{t0, (long)nA, 1.f, 0.f}, nG, nA, nA, st));
         // out = QG T2
-        KFACB_CHECK_CUDA(launch_gemm(LdKContig{QG[i], (long)nG, nG, nG},
+        KFACB_CHECK_CUDA(launch_gemm_auto(LdKContig{QG[i], (long)nG, nG, nG},
                                      LdMnContig{t0, (long)nA, nA, nG},
                                      EpiStore{out[i], (long)nA, 1.f, 0.f}, nG, nA, nG, st));
     }
@@ -188,11 +189,11 @@ extern "C" int kfacb_precond_inverse(const kfacb_layer_t* layers, int32_t count,
         KFACB_REQUIRE(invA[i] && invG[i] && out[i] && (!l.has_bias || bgrad[i]), "layer %d: null pointer", i);
         const int dW = nA - (l.has_bias ? 1 : 0);
         // T = grad invA
-        KFACB_CHECK_CUDA(launch_gemm(LdGrad{wgrad[i], bgrad[i], nG, dW, nA},
+        KFACB_CHECK_CUDA(launch_gemm_auto(LdGrad{wgrad[i], bgrad[i], nG, dW, nA},
                                      LdMnContig{invA[i], (long)nA, nA, nA},
                                      EpiStore{t0, (long)nA, 1.f, 0.f}, nG, nA, nA, st));
         // out = invG T
-        KFACB_CHECK_CUDA(launch_gemm(LdKContig{invG[i], (long)nG, nG, nG},
+        KFACB_CHECK_CUDA(launch_gemm_auto(LdKContig{invG[i], (long)nG, nG, nG},
                                      LdMnContig{t0, (long)nA, nA, nG},
                                      EpiStore{out[i], (long)nA, 1.f, 0.f}, nG, nA, nG, st));
     }

@@ -1,0 +1,192 @@
+// tc_gemm.cuh -- generic tcgen05 3xTF32 GEMM core:  D(128x128, TMEM) = sum_k A(m,k) B(n,k)
+// with operands described by the same loader functors as the SIMT core (common.cuh).
+//
+// CTA = 256 threads.  Per 32-wide k-slab every thread gathers 4 k-quads of A and 4 of B
+// (coalesced: lanes walk k for K_FAST loaders, rows otherwise), splits them into tf32 hi/lo and
+// stores 16-byte units into the no-swizzle K-major core-matrix layout
+//     (row, k) -> (row & 7) * 16 + (row >> 3) * 128 + (k >> 2) * LBO + (k & 3) * 4
+// One thread issues 3 passes x 4 UMMAs (M = N = 128, K = 8) per slab into a 128-column fp32 TMEM
+// accumulator and commits to an mbarrier; the gathers of slab s+1 are in flight meanwhile.
+// The accumulator is drained through shared memory so that epilogues run with lanes along n
+// (coalesced global access, conflict-free transposed reads for mirrored stores).
+#pragma once
+#include "common.cuh"
+#include "tc.cuh"
+
+namespace kfacb {
+namespace tcg {
+
+constexpr int THREADS = 256;
+constexpr int BKS = 32;                                  // k-slab
+constexpr int SBO = 128;
+constexpr int LBO = (TILE / 8) * 128 + 16;               // 2064 (+16: conflict-free staging stores)
+constexpr int PART = (BKS / 4) * LBO;                    // 16512 bytes per operand part
+constexpr int SMEM = 4 * PART;                           // A_hi, A_lo, B_hi, B_lo = 66048 = 128 * 129 * 4
+constexpr int DPITCH = TILE + 1;                         // drained accumulator pitch (floats)
+static_assert(SMEM >= TILE * DPITCH * 4, "drain buffer must fit in the operand buffers");
+
+struct Ctx {
+    unsigned char* dsm;
+    uint64_t* mbar;
+    uint32_t tmem;
+    int slabs_done;       // slabs committed so far (mbarrier phase bookkeeping)
+};
+
+// call at kernel start (all threads); `tmem_slot` and `mbar` live in static shared memory
+__device__ __forceinline__ void setup(Ctx& c, unsigned char* dsm, uint64_t* mbar, uint32_t* tmem_slot) {
+    if (threadIdx.x == 0) { tc::mbar_init(mbar, 1); tc::fence_mbar_init(); }
+    if ((threadIdx.x >> 5) == 0) tc::tmem_alloc<128>(tmem_slot);
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    c.dsm = dsm; c.mbar = mbar; c.tmem = *tmem_slot; c.slabs_done = 0;
+}
+__device__ __forceinline__ void teardown(Ctx& c) {
+    tc::tc_fence_before();
+    __syncthreads();
+    if ((threadIdx.x >> 5) == 0) tc::tmem_dealloc<128>(c.tmem);
+}
+
+template <class L>
+__device__ __forceinline__ void fetch(const L& ld, int mn0, int k0, float4 (&r)[4]) {
+    const int tid = threadIdx.x;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int idx = tid + THREADS * i;
+        int row, kq;
+        if (L::K_FAST) { kq = idx & 7; row = idx >> 3; } else { row = idx & 127; kq = idx >> 7; }
+        const int k = k0 + 4 * kq;
+        r[i].x = ld(mn0 + row, k); r[i].y = ld(mn0 + row, k + 1);
+        r[i].z = ld(mn0 + row, k + 2); r[i].w = ld(mn0 + row, k + 3);
+    }
+}
+template <class L>
+__device__ __forceinline__ void stage(unsigned char* hi_base, unsigned char* lo_base, const float4 (&r)[4]) {
+    const int tid = threadIdx.x;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int idx = tid + THREADS * i;
+        int row, kq;
+        if (L::K_FAST) { kq = idx & 7; row = idx >> 3; } else { row = idx & 127; kq = idx >> 7; }
+        const int off = (row & 7) * 16 + (row >> 3) * SBO + kq * LBO;
+        float4 hi, lo;
+        tc::split_tf32(r[i], hi, lo);
+        *reinterpret_cast<float4*>(hi_base + off) = hi;
+        *reinterpret_cast<float4*>(lo_base + off) = lo;
+    }
+}
+
+// accumulate over k in [kbeg, kend) into TMEM columns [0,128); returns when the accumulator is complete
+template <class LA, class LB>
+__device__ __forceinline__ void mainloop(const LA& la, const LB& lb, int m0, int n0, int kbeg, int kend,
+                                         bool same_operand, Ctx& c) {
+    unsigned char* a_hi = c.dsm;
+    unsigned char* a_lo = c.dsm + PART;
+    unsigned char* b_hi = same_operand ? a_hi : c.dsm + 2 * PART;
+    unsigned char* b_lo = same_operand ? a_lo : c.dsm + 3 * PART;
+    float4 ra[4], rb[4];
+    const int nslab = (kend - kbeg + BKS - 1) / BKS;
+    if (nslab > 0) { fetch(la, m0, kbeg, ra); if (!same_operand) fetch(lb, n0, kbeg, rb); }
+    constexpr uint32_t idesc = tc::idesc_tf32(128, 128, 0, 0);
+    for (int s = 0; s < nslab; ++s) {
+        if (c.slabs_done > 0) tc::mbar_wait(c.mbar, (uint32_t)((c.slabs_done - 1) & 1));   // smem free again
+        stage<LA>(a_hi, a_lo, ra);
+        if (!same_operand) stage<LB>(b_hi, b_lo, rb);
+        if (s + 1 < nslab) {
+            fetch(la, m0, kbeg + (s + 1) * BKS, ra);
+            if (!same_operand) fetch(lb, n0, kbeg + (s + 1) * BKS, rb);
+        }
+        tc::fence_async_smem();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            tc::tc_fence_after();
+            const uint32_t ah = tc::smem_u32(a_hi), al = tc::smem_u32(a_lo);
+            const uint32_t bh = tc::smem_u32(b_hi), bl = tc::smem_u32(b_lo);
+#pragma unroll
+            for (int pass = 0; pass < 3; ++pass) {
+                const uint32_t ab = pass == 1 ? al : ah;
+                const uint32_t bb = pass == 2 ? bl : bh;
+#pragma unroll
+                for (int j = 0; j < BKS / 8; ++j) {
+                    const uint64_t ad = tc::smem_desc(ab + 2 * j * LBO, LBO, SBO);
+                    const uint64_t bd = tc::smem_desc(bb + 2 * j * LBO, LBO, SBO);
+                    tc::umma_tf32(c.tmem, ad, bd, idesc, !(s == 0 && pass == 0 && j == 0));
+                }
+            }
+            tc::umma_commit(c.mbar);
+        }
+        c.slabs_done += 1;
+    }
+    if (c.slabs_done > 0) tc::mbar_wait(c.mbar, (uint32_t)((c.slabs_done - 1) & 1));
+    tc::tc_fence_after();
+}
+
+// TMEM accumulator (lane = m, column = n) -> shared memory float[128][DPITCH] (overwrites the operand buffers)
+__device__ __forceinline__ float* drain(Ctx& c, bool has_data) {
+    float* d = reinterpret_cast<float*>(c.dsm);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m = 32 * (warp & 3) + lane;
+    const int cbase = (warp >> 2) * 64;                  // warps 0-3: columns 0-63, warps 4-7: 64-127
+    float v[32];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        if (has_data) {
+            tc::tmem_ld32(c.tmem + ((uint32_t)(32 * (warp & 3)) << 16) + cbase + 32 * h, v);
+        } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = 0.f;
+        }
+#pragma unroll
+        for (int i = 0; i < 32; ++i) d[m * DPITCH + cbase + 32 * h + i] = v[i];
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    return d;
+}
+
+// generic GEMM: C(m, n) = epi(m, n, sum_k A(m,k) B(n,k)); grid (tiles_n, tiles_m)
+template <class LA, class LB, class Epi>
+__global__ void __launch_bounds__(THREADS)
+tc_gemm_kernel(LA la, LB lb, Epi epi, int M, int N, int K) {
+    extern __shared__ __align__(128) unsigned char dsm_raw[];
+    __shared__ __align__(8) uint64_t mbar;
+    __shared__ uint32_t tmem_slot;
+    Ctx c;
+    setup(c, dsm_raw, &mbar, &tmem_slot);
+    const int m0 = blockIdx.y * TILE, n0 = blockIdx.x * TILE;
+    mainloop(la, lb, m0, n0, 0, K, false, c);
+    const float* d = drain(c, K > 0);
+    for (int e = threadIdx.x; e < TILE * TILE; e += THREADS) {
+        const int m = e >> 7, n = e & 127;
+        if (m0 + m < M && n0 + n < N) epi(m0 + m, n0 + n, d[m * DPITCH + n]);
+    }
+    teardown(c);
+}
+
+template <class LA, class LB, class Epi>
+static inline cudaError_t launch(const LA& la, const LB& lb, const Epi& epi, int M, int N, int K, cudaStream_t st) {
+    static bool attr_done = false;       // per template instantiation
+    if (!attr_done) {
+        cudaError_t e = cudaFuncSetAttribute(tc_gemm_kernel<LA, LB, Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+        if (e != cudaSuccess) return e;
+        attr_done = true;
+    }
+    dim3 grid(cdiv(N, TILE), cdiv(M, TILE));
+    tc_gemm_kernel<LA, LB, Epi><<<grid, THREADS, SMEM, st>>>(la, lb, epi, M, N, K);
+    count_launch();
+    return cudaGetLastError();
+}
+
+}  // namespace tcg
+
+bool use_tc_gemm();   // false when KFACB_GEMM_SIMT=1 (debug / A-B comparisons)
+
+// dispatch: tensor cores unless the problem is tiny or the SIMT path is forced
+template <class LA, class LB, class Epi>
+static inline cudaError_t launch_gemm_auto(const LA& la, const LB& lb, const Epi& epi, int M, int N, int K,
+                                           cudaStream_t st) {
+    if (use_tc_gemm() && (long)M * N >= 64 * 64 && K >= 32) return tcg::launch(la, lb, epi, M, N, K, st);
+    return launch_gemm(la, lb, epi, M, N, K, st);
+}
+
+}  // namespace kfacb
