@@ -1140,10 +1140,10 @@ extern "C" int kfacb_eigh_batched(const int32_t* n, int32_t count,
             const BjMat& b = hm[k];
             const long ld = 2L * b.n_pad;
             LdKContig lv{b.X + b.n_pad, ld, b.n, b.n};
-            KFACB_CHECK_CUDA(launch_gemm_auto(lv, lv, EpiGramMinusI{b.X, ld}, b.n, b.n, b.n, st));
+            KFACB_CHECK_CUDA(launch_gemm(lv, lv, EpiGramMinusI{b.X, ld}, b.n, b.n, b.n, st));   // V V^T - I cancels to ~1e-6: exact fp32 FMAs, not 3xTF32
             LdKContig le{b.X, ld, b.n, b.n};
             LdMnContig lvt{b.X + b.n_pad, ld, b.n, b.n};
-            KFACB_CHECK_CUDA(launch_gemm_auto(le, lvt, EpiNsUpdate{b.Q, b.X, ld, b.n, b.n_pad}, b.n, b.n, b.n, st));
+            KFACB_CHECK_CUDA(launch_gemm(le, lvt, EpiNsUpdate{b.Q, b.X, ld, b.n, b.n_pad}, b.n, b.n, b.n, st));
             KFACB_CHECK_CUDA(cudaMemcpy2DAsync(b.X + b.n_pad, ld * sizeof(float), b.Q, (size_t)b.n * sizeof(float),
                                                (size_t)b.n * sizeof(float), b.n, cudaMemcpyDeviceToDevice, st));
         }
@@ -1154,7 +1154,7 @@ extern "C" int kfacb_eigh_batched(const int32_t* n, int32_t count,
         LdKContig la{b.X + b.n_pad, 2L * b.n_pad, b.n, b.n};
         LdMnContig lb{b.A, (long)b.n, b.n, b.n};
         EpiToX epi{b.X, 2L * b.n_pad};
-        KFACB_CHECK_CUDA(launch_gemm_auto(la, lb, epi, b.n, b.n, b.n, st));
+        KFACB_CHECK_CUDA(launch_gemm(la, lb, epi, b.n, b.n, b.n, st));
     }
     int nmax = 0;
     for (int k = 0; k < nb; ++k) if (hm[k].n > nmax) nmax = hm[k].n;

@@ -63,7 +63,8 @@ def test_factor_conv(eng, cfg, first):
     curG = torch.eye(d.dG, dtype=torch.float64) if first else G0.double()
     refA = orc.running_average(orc.factor_A(a.double(), spec), curA, 0.95)
     refG = orc.running_average(orc.factor_G(g.double(), spec), curG, 0.95)
-    assert _rel(A, refA) < 2e-6 and _rel(G, refG) < 2e-6
+    # 3xTF32 tensor-core accumulation: ~5e-7 of sum|a||b| per entry (fp32 SGEMM: ~1e-7); bar = 6e-6 << 1e-4
+    assert _rel(A, refA) < 6e-6 and _rel(G, refG) < 6e-6
     assert torch.equal(A, A.t()) and torch.equal(G, G.t())      # exactly symmetric
 
 
@@ -83,7 +84,7 @@ def test_factor_linear(eng, cfg):
     eng.factor_update([d], [a.to(DEV)], [g.to(DEV)], [A], [G], 0.95, True)
     refA = orc.running_average(orc.factor_A(a.double(), spec), torch.eye(d.dA, dtype=torch.float64), 0.95)
     refG = orc.running_average(orc.factor_G(g.double(), spec), torch.eye(d.dG, dtype=torch.float64), 0.95)
-    assert _rel(A, refA) < 2e-6 and _rel(G, refG) < 2e-6
+    assert _rel(A, refA) < 6e-6 and _rel(G, refG) < 6e-6
     # skipping: NULL a leaves A untouched
     A2 = A.clone()
     eng.factor_update([d], [None], [g.to(DEV)], [A2], [G], 0.95, False)
