@@ -154,7 +154,10 @@ tc_syrk_ema_kernel(L ld, int n, int K, int kchunk, float scale, float alpha, int
             const int m = m0 + (e >> 7), cc = c0 + (e & 127);
             if (m < n && cc < n) {
                 const float old = first_step ? (m == cc ? 1.f : 0.f) : factor[(long)m * n + cc];
-                factor[(long)m * n + cc] = fmaf(alpha, scale * d[(e >> 7) * tcg::DPITCH + (e & 127)], keep * old);
+                // diagonal tiles: take both (m, cc) and (cc, m) from the upper triangle => exactly symmetric factor
+                const int r = e >> 7, q = e & 127;
+                const float v = (ti == tj && r > q) ? d[q * tcg::DPITCH + r] : d[r * tcg::DPITCH + q];
+                factor[(long)m * n + cc] = fmaf(alpha, scale * v, keep * old);
             }
         }
         if (ti != tj) {          // mirrored tile: element (cc, m) takes the value computed for (m, cc)
@@ -183,8 +186,10 @@ __global__ void syrk_reduce_ema_kernel(const float* __restrict__ partial, int ks
     const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= (long)n * n) return;
     const int i = (int)(idx / n), j = (int)(idx - (long)i * n);
-    const int r = (i / TILE <= j / TILE) ? i : j;
-    const int c = (i / TILE <= j / TILE) ? j : i;
+    // read the upper-triangular element (tile-wise, and element-wise inside diagonal tiles): exact symmetry
+    const bool upper = (i / TILE < j / TILE) || (i / TILE == j / TILE && i <= j);
+    const int r = upper ? i : j;
+    const int c = upper ? j : i;
     float s = 0.f;
     for (int z = 0; z < ksplit; ++z) s += partial[(long)z * n * n + (long)r * n + c];
     const float old = first_step ? (i == j ? 1.f : 0.f) : factor[idx];
