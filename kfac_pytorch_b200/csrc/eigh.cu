@@ -7,17 +7,18 @@
 //   n <= 128 : one CTA per matrix, two-sided cyclic Jacobi with the round-robin
 //              parallel ordering, matrix and eigenvector accumulator resident
 //              in shared memory.
-//   n  > 128 : blocked ONE-SIDED (Hestenes) Jacobi.  The work array
+//   n  > 128 : implicit two-sided BLOCK Jacobi.  The work array
 //              X = [W^T | V^T] (n_pad x 2 n_pad, row i = column i of W = A V and
-//              of V) starts as [A | I].  A round pairs up 32-row blocks with the
-//              round-robin schedule; per pair: 64x64 Gram of the W rows
-//              (split-K), two-sided Jacobi of the Gram in shared memory -> U,
-//              rows <- U^T rows (W and V together).  All pairs of all matrices
-//              of the batch run in the same launches.  At convergence the W
-//              rows are mutually orthogonal: W = V diag(lambda).  Eigenvalues
-//              are then recomputed as Rayleigh quotients v^T A v (second-order
-//              accurate), sorted ascending, floored, and V is written out
-//              column-wise.
+//              of V) starts as [A | I].  A round pairs up 64-row blocks with the
+//              round-robin schedule; per pair: the 128x128 projected block
+//              H = V_R^T A V_R = V_R W_R^T (tcgen05 3xTF32, split-K), one cyclic
+//              Jacobi sweep of H in shared memory -> U, rows <- U^T rows (W and V
+//              together, tcgen05 3xTF32).  All pairs of all matrices of the batch
+//              run in the same launches.  After convergence V is re-orthogonalised
+//              (one Newton-Schulz step), eigenvalues are recomputed as Rayleigh
+//              quotients v^T A v, sorted ascending, floored, and V is written out
+//              column-wise.  Working on H (not on the Gram W_R W_R^T of one-sided
+//              Hestenes Jacobi) avoids squaring the condition number.
 #include <stdlib.h>
 #include "common.cuh"
 #include "tc_gemm.cuh"
@@ -25,9 +26,10 @@
 
 namespace kfacb {
 
-constexpr int BJ_B = 32;              // rows per block
-constexpr int BJ_M = 2 * BJ_B;        // rows per pair = size of the inner eigenproblem
-constexpr int BJ_KCHUNK = 256;        // Gram split-K chunk
+constexpr int BJ_B = 64;              // rows per block
+constexpr int BJ_M = 2 * BJ_B;        // rows per pair = size of the inner eigenproblem (= TILE)
+constexpr int BJ_KCHUNK = 512;        // split-K chunk of the projected-block GEMM
+static_assert(BJ_M == TILE, "a pair is one 128-row GEMM tile");
 constexpr int BJ_MAX_SWEEPS = 16;
 constexpr int BJ_INNER_SWEEPS = 1;    // cap of Jacobi sweeps on the 64x64 Gram per visit
 constexpr int DIRECT_MAX_N = 128;
@@ -255,80 +257,44 @@ __global__ void bj_init_kernel(const BjMat* mats, BjState* state) {
     if ((threadIdx.x & 31) == 0 && ss > 0.f) atomicAdd(&state[blockIdx.y].norm2, ss);
 }
 
-// Projected block H = V_R^T A V_R = V_R W_R^T (64x64) of one pair over one k-chunk (SIMT
-// fp32 version; the tensor-core version is bj_h_tc_kernel).  grid (total_pairs, max ksplit)
-__global__ void __launch_bounds__(256)
-bj_gram_kernel(const BjMat* mats, const int* pair_mat, const BjState* state, int round,
-               float* __restrict__ partial, const long* partial_off) {
-    __shared__ float vs[BK][BJ_M + 4];
-    __shared__ float ws[BK][BJ_M + 4];
-    const int mi = pair_mat[blockIdx.x];
-    const BjMat mt = mats[mi];
-    if (state[mi].converged || (int)blockIdx.y >= mt.ksplit) return;
-    int bi, bj;
-    if (!bj_pair_blocks(mt, blockIdx.x - mt.pair_begin, round, bi, bj)) return;
-    const long ld = 2L * mt.n_pad;
-    const int kbeg = blockIdx.y * BJ_KCHUNK, kend = min(mt.n_pad, kbeg + BJ_KCHUNK);
-    const int tid = threadIdx.x, kk = tid & 31, rr = tid >> 5;
-    const int tx = tid & 15, ty = tid >> 4;
-    float acc[4][4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-    const float* rowp[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        const int r = rr + 8 * i;
-        const int grow = (r < BJ_B) ? bi * BJ_B + r : bj * BJ_B + (r - BJ_B);
-        rowp[i] = mt.X + (long)grow * ld;
-    }
-    float rw[8], rv[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) { rw[i] = rowp[i][kbeg + kk]; rv[i] = rowp[i][mt.n_pad + kbeg + kk]; }
-    for (int k0 = kbeg; k0 < kend; k0 += BK) {
-        __syncthreads();
-#pragma unroll
-        for (int i = 0; i < 8; ++i) { ws[kk][rr + 8 * i] = rw[i]; vs[kk][rr + 8 * i] = rv[i]; }
-        __syncthreads();
-        if (k0 + BK < kend) {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) { rw[i] = rowp[i][k0 + BK + kk]; rv[i] = rowp[i][mt.n_pad + k0 + BK + kk]; }
-        }
-#pragma unroll
-        for (int k = 0; k < BK; ++k) {
-            const float4 a = *reinterpret_cast<const float4*>(&vs[k][ty * 4]);
-            const float4 b = *reinterpret_cast<const float4*>(&ws[k][tx * 4]);
-            const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-#pragma unroll
-                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
-        }
-    }
-    float* dst = partial + partial_off[mi] +
-                 ((long)(blockIdx.x - mt.pair_begin) * mt.ksplit + blockIdx.y) * (BJ_M * BJ_M);
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-        *reinterpret_cast<float4*>(&dst[(ty * 4 + i) * BJ_M + tx * 4]) =
-            make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
-}
-
 // ---------------------------------------------------------------------------
-// tensor-core (tcgen05, 3xTF32) versions of the two GEMMs of a Jacobi round
+// The three kernels of a Jacobi round.  Blocks are 64 rows, a pair is 128 rows: the two GEMMs are
+// 128x128-tile tcgen05 3xTF32 products on the shared core of tc_gemm.cuh, the 128x128 projected
+// problem is solved in shared memory.
 // ---------------------------------------------------------------------------
-constexpr int TC_THREADS = 128;
-// H kernel: K-major operands, 64-k slabs.  element (m, k): (m&7)*16 + (m>>3)*128 + (k>>2)*LBO + (k&3)*4
-constexpr int H_SLAB = 64;
-constexpr int H_LBO = 8 * 128 + 16;                 // +16 B pad: conflict-free staging stores
-constexpr int H_SBO = 128;
-constexpr int H_PART = (H_SLAB / 4) * H_LBO;        // bytes of one operand part (hi or lo)
-constexpr int H_SMEM = 4 * H_PART;
+// rows of a pair viewed as a 128 x K operand (k contiguous): rows 0-63 = block bi, 64-127 = block bj
+struct LdPairRows {
+    static constexpr bool K_FAST = true;
+    const float* base; long ld; int row_a, row_b; int kend;
+    __device__ __forceinline__ float operator()(int mn, int k) const {
+        if (k >= kend) return 0.f;
+        const int grow = mn < BJ_B ? row_a + mn : row_b + (mn - BJ_B);
+        return __ldg(base + (long)grow * ld + k);
+    }
+};
+// columns of the pair's rows viewed as a (128 columns) x (128 rows-as-k) operand (column index contiguous)
+struct LdPairCols {
+    static constexpr bool K_FAST = false;
+    const float* X; long ld; int row_a, row_b; long c0;
+    __device__ __forceinline__ float operator()(int mn, int k) const {
+        const long c = c0 + mn;
+        if (c >= ld) return 0.f;
+        const int grow = k < BJ_B ? row_a + k : row_b + (k - BJ_B);
+        return X[(long)grow * ld + c];          // plain load: X is rewritten in place by this kernel
+    }
+};
+// U (128x128 row-major, U[k][i]) as operand B(n = i, k)
+struct LdUmat {
+    static constexpr bool K_FAST = false;
+    const float* U;
+    __device__ __forceinline__ float operator()(int mn, int k) const { return __ldg(U + k * BJ_M + mn); }
+};
 
-__global__ void __launch_bounds__(TC_THREADS)
+// (1) H = V_R^T A V_R = V_R W_R^T (128x128) over one k-chunk.  grid (total_pairs, max ksplit)
+__global__ void __launch_bounds__(tcg::THREADS)
 bj_h_tc_kernel(const BjMat* mats, const int* pair_mat, const BjState* state, int round,
                float* __restrict__ partial, const long* partial_off) {
-    extern __shared__ __align__(128) unsigned char dsm[];
+    extern __shared__ __align__(128) unsigned char dsm_raw[];
     __shared__ __align__(8) uint64_t mbar;
     __shared__ uint32_t tmem_slot;
     const int mi = pair_mat[blockIdx.x];
@@ -336,252 +302,72 @@ bj_h_tc_kernel(const BjMat* mats, const int* pair_mat, const BjState* state, int
     if (state[mi].converged || (int)blockIdx.y >= mt.ksplit) return;
     int bi, bj;
     if (!bj_pair_blocks(mt, blockIdx.x - mt.pair_begin, round, bi, bj)) return;
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    if (tid == 0) { tc::mbar_init(&mbar, 1); tc::fence_mbar_init(); }
-    if (warp == 0) tc::tmem_alloc<64>(&tmem_slot);
-    tc::tc_fence_before();
-    __syncthreads();
-    tc::tc_fence_after();
-    const uint32_t tmem = tmem_slot;
-    unsigned char* a_hi = dsm;                    // V rows
-    unsigned char* a_lo = dsm + H_PART;
-    unsigned char* b_hi = dsm + 2 * H_PART;       // W rows
-    unsigned char* b_lo = dsm + 3 * H_PART;
+    tcg::Ctx c;
+    tcg::setup(c, dsm_raw, &mbar, &tmem_slot);
     const long ld = 2L * mt.n_pad;
     const int kbeg = blockIdx.y * BJ_KCHUNK, kend = min(mt.n_pad, kbeg + BJ_KCHUNK);
-    const int nslab = (kend - kbeg + H_SLAB - 1) / H_SLAB;
-    constexpr uint32_t idesc = tc::idesc_tf32(64, 64, 0, 0);
-    float4 va[8], wa[8];
-    const float* rbase[8];
-    int soff[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        const int idx = tid + TC_THREADS * i;
-        const int kq = idx & 15, r = idx >> 4;
-        const int grow = (r < BJ_B) ? bi * BJ_B + r : bj * BJ_B + (r - BJ_B);
-        rbase[i] = mt.X + (long)grow * ld + kq * 4;
-        soff[i] = (r & 7) * 16 + (r >> 3) * H_SBO + kq * H_LBO;
-    }
-    auto load_slab = [&](int s) {
-        const int k0 = kbeg + s * H_SLAB;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const int kq = (tid + TC_THREADS * i) & 15;
-            const bool ok = k0 + kq * 4 < kend;
-            wa[i] = ok ? *reinterpret_cast<const float4*>(rbase[i] + k0) : make_float4(0.f, 0.f, 0.f, 0.f);
-            va[i] = ok ? *reinterpret_cast<const float4*>(rbase[i] + k0 + mt.n_pad) : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-    };
-    load_slab(0);
-    for (int s = 0; s < nslab; ++s) {
-        if (s > 0) tc::mbar_wait(&mbar, (uint32_t)((s - 1) & 1));   // MMAs of the previous slab done reading smem
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            float4 hi, lo;
-            tc::split_tf32(va[i], hi, lo);
-            *reinterpret_cast<float4*>(a_hi + soff[i]) = hi;
-            *reinterpret_cast<float4*>(a_lo + soff[i]) = lo;
-            tc::split_tf32(wa[i], hi, lo);
-            *reinterpret_cast<float4*>(b_hi + soff[i]) = hi;
-            *reinterpret_cast<float4*>(b_lo + soff[i]) = lo;
-        }
-        if (s + 1 < nslab) load_slab(s + 1);        // in flight during the barrier, the MMAs and the next wait
-        tc::fence_async_smem();
-        __syncthreads();
-        if (tid == 0) {
-            tc::tc_fence_after();
-            const uint32_t ah = tc::smem_u32(a_hi), al = tc::smem_u32(a_lo);
-            const uint32_t bh = tc::smem_u32(b_hi), bl = tc::smem_u32(b_lo);
-#pragma unroll
-            for (int pass = 0; pass < 3; ++pass) {
-                const uint32_t ab = pass == 1 ? al : ah;
-                const uint32_t bb = pass == 2 ? bl : bh;
-#pragma unroll
-                for (int j = 0; j < H_SLAB / 8; ++j) {
-                    const uint64_t ad = tc::smem_desc(ab + 2 * j * H_LBO, H_LBO, H_SBO);
-                    const uint64_t bd = tc::smem_desc(bb + 2 * j * H_LBO, H_LBO, H_SBO);
-                    tc::umma_tf32(tmem, ad, bd, idesc, !(s == 0 && pass == 0 && j == 0));
-                }
-            }
-            tc::umma_commit(&mbar);
-        }
-    }
-    tc::mbar_wait(&mbar, (uint32_t)((nslab - 1) & 1));
-    tc::tc_fence_after();
-    // D (64x64, M=64 layout): row m lives in TMEM lane (m & 15) + 32 * (m >> 4)
-    float v0[32], v1[32];
-    const uint32_t taddr = tmem + ((uint32_t)(32 * warp) << 16);
-    tc::tmem_ld32(taddr, v0);
-    tc::tmem_ld32(taddr + 32, v1);
-    if (lane < 16) {
-        float* dst = partial + partial_off[mi] +
-                     ((long)(blockIdx.x - mt.pair_begin) * mt.ksplit + blockIdx.y) * (BJ_M * BJ_M) +
-                     (16 * warp + lane) * BJ_M;
-#pragma unroll
-        for (int c = 0; c < 32; c += 4) {
-            *reinterpret_cast<float4*>(dst + c) = make_float4(v0[c], v0[c + 1], v0[c + 2], v0[c + 3]);
-            *reinterpret_cast<float4*>(dst + 32 + c) = make_float4(v1[c], v1[c + 1], v1[c + 2], v1[c + 3]);
-        }
-    }
-    tc::tc_fence_before();
-    __syncthreads();
-    if (warp == 0) tc::tmem_dealloc<64>(tmem);
+    LdPairRows lv{mt.X + mt.n_pad, ld, bi * BJ_B, bj * BJ_B, kend};      // V rows
+    LdPairRows lw{mt.X, ld, bi * BJ_B, bj * BJ_B, kend};                 // W rows
+    tcg::mainloop(lv, lw, 0, 0, kbeg, kend, false, c);
+    const float* d = tcg::drain(c, true);
+    float* dst = partial + partial_off[mi] +
+                 ((long)(blockIdx.x - mt.pair_begin) * mt.ksplit + blockIdx.y) * (BJ_M * BJ_M);
+    for (int e = threadIdx.x; e < BJ_M * BJ_M; e += tcg::THREADS)
+        dst[e] = d[(e >> 7) * tcg::DPITCH + (e & 127)];
+    tcg::teardown(c);
 }
 
-// update kernel (transposed product): D[c][i] = sum_k X[r_k][c] U[k][i]; M = 128 columns of X,
-// N = 64, K = 64.  Both operands are staged K-MAJOR (the layout validated by tools/tc_selftest.cu):
-// each thread gathers 4 consecutive k of ONE column (4 coalesced 32-bit loads across the warp)
-// and stores them as one 16-byte unit:  (mn, k): (mn&7)*16 + (mn>>3)*128 + (k>>2)*LBO + (k&3)*4
-constexpr int U_SBO = 128;
-constexpr int U_LBO_A = (TILE / 8) * 128;           // 2048
-constexpr int U_LBO_B = (BJ_M / 8) * 128;           // 1024
-constexpr int U_PART_A = (BJ_M / 4) * U_LBO_A;      // 32768
-constexpr int U_PART_B = (BJ_M / 4) * U_LBO_B;      // 16384
-constexpr int U_SMEM = 2 * U_PART_A + 2 * U_PART_B; // 98304
-
-// One CTA owns `tiles_per_cta` consecutive 128-column tiles of one pair: U is staged once, the
-// X loads of tile t+1 are in flight while the tensor core works on tile t and the epilogue of
-// tile t-1 drains the other TMEM accumulator (2 x 64 columns, double buffered).
-__global__ void __launch_bounds__(TC_THREADS)
+// (3) rows <- U^T rows for the 128 rows of a pair (W and V halves together), 128 columns per CTA:
+//     D[c][i] = sum_k X[r_k][c] U[k][i].  grid (col tiles, total_pairs)
+__global__ void __launch_bounds__(tcg::THREADS)
 bj_update_tc_kernel(const BjMat* mats, const int* pair_mat, const BjState* state, int round,
-                    const float* __restrict__ ubuf, int tiles_per_cta, int reverse) {
-    extern __shared__ __align__(128) unsigned char dsm[];
-    __shared__ __align__(8) uint64_t mbar[2];
+                    const float* __restrict__ ubuf) {
+    extern __shared__ __align__(128) unsigned char dsm_raw[];
+    __shared__ __align__(8) uint64_t mbar;
     __shared__ uint32_t tmem_slot;
-    // reverse = walk the pairs in the opposite order to the H kernel of the same round: the rows it read
-    // last are still in L2 when the update starts (X of a 4608-dim factor is 170 MB vs 126 MB of L2)
-    const int pair_idx = reverse ? (int)(gridDim.y - 1 - blockIdx.y) : (int)blockIdx.y;
+    const int pair_idx = blockIdx.y;
     const int mi = pair_mat[pair_idx];
     const BjMat mt = mats[mi];
     const long ld = 2L * mt.n_pad;
-    const int tile0 = blockIdx.x * tiles_per_cta;
-    if (state[mi].converged || (long)tile0 * TILE >= ld) return;
+    const long c0 = (long)blockIdx.x * TILE;
+    if (state[mi].converged || c0 >= ld) return;
     int bi, bj;
     if (!bj_pair_blocks(mt, pair_idx - mt.pair_begin, round, bi, bj)) return;
-    const int ntiles = min(tiles_per_cta, (int)((ld - (long)tile0 * TILE + TILE - 1) / TILE));
-    const int tid = threadIdx.x, warp = tid >> 5;
-    if (tid == 0) { tc::mbar_init(&mbar[0], 1); tc::mbar_init(&mbar[1], 1); tc::fence_mbar_init(); }
-    if (warp == 0) tc::tmem_alloc<128>(&tmem_slot);
-    tc::tc_fence_before();
-    __syncthreads();
-    tc::tc_fence_after();
-    const uint32_t tmem = tmem_slot;
-    unsigned char* a_hi = dsm;
-    unsigned char* a_lo = dsm + U_PART_A;
-    unsigned char* b_hi = dsm + 2 * U_PART_A;
-    unsigned char* b_lo = dsm + 2 * U_PART_A + U_PART_B;
-    const float* rowp[BJ_M / 4];                     // first row of each k-quad (a quad never straddles the 2 blocks)
-#pragma unroll
-    for (int kq = 0; kq < BJ_M / 4; ++kq) {
-        const int k = 4 * kq;
-        const int grow = (k < BJ_B) ? bi * BJ_B + k : bj * BJ_B + (k - BJ_B);
-        rowp[kq] = mt.X + (long)grow * ld;
-    }
-    float x[BJ_M];
-    auto load_tile = [&](int t) {
-        const long c = (long)(tile0 + t) * TILE + tid;
-        if (c < ld) {
-#pragma unroll
-            for (int kq = 0; kq < BJ_M / 4; ++kq) {
-                const float* src = rowp[kq] + c;
-                x[4 * kq] = src[0]; x[4 * kq + 1] = src[ld]; x[4 * kq + 2] = src[2 * ld]; x[4 * kq + 3] = src[3 * ld];
-            }
-        } else {
-#pragma unroll
-            for (int k = 0; k < BJ_M; ++k) x[k] = 0.f;
-        }
-    };
-    load_tile(0);
-    // U: column i, k-quads (tid>>6) + 2t
-    {
-        const float* usrc = ubuf + (long)pair_idx * (BJ_M * BJ_M);
-        const int i = tid & 63;
-        const int boff = (i & 7) * 16 + (i >> 3) * U_SBO;
-#pragma unroll
-        for (int t = 0; t < BJ_M / 8; ++t) {
-            const int kq = (tid >> 6) + 2 * t;
-            const float* src = usrc + (4 * kq) * BJ_M + i;
-            float4 u;
-            u.x = src[0]; u.y = src[BJ_M]; u.z = src[2 * BJ_M]; u.w = src[3 * BJ_M];
-            float4 hi, lo;
-            tc::split_tf32(u, hi, lo);
-            *reinterpret_cast<float4*>(b_hi + boff + kq * U_LBO_B) = hi;
-            *reinterpret_cast<float4*>(b_lo + boff + kq * U_LBO_B) = lo;
+    tcg::Ctx c;
+    tcg::setup(c, dsm_raw, &mbar, &tmem_slot);
+    LdPairCols la{mt.X, ld, bi * BJ_B, bj * BJ_B, c0};
+    LdUmat lb{ubuf + (long)pair_idx * (BJ_M * BJ_M)};
+    tcg::mainloop(la, lb, 0, 0, 0, BJ_M, false, c);          // the whole input tile is consumed here ...
+    const float* d = tcg::drain(c, true);
+    for (int e = threadIdx.x; e < BJ_M * TILE; e += tcg::THREADS) {   // ... before it is overwritten in place
+        const int i = e >> 7, cc = e & 127;                  // lanes along the column: coalesced stores,
+        if (c0 + cc < ld) {                                  // conflict-free transposed read of d[cc][i]
+            const int grow = i < BJ_B ? bi * BJ_B + i : bj * BJ_B + (i - BJ_B);
+            mt.X[(long)grow * ld + c0 + cc] = d[cc * tcg::DPITCH + i];
         }
     }
-    const int aoff = (tid & 7) * 16 + (tid >> 3) * U_SBO;
-    auto epilogue = [&](int t) {                     // D[c][i]: TMEM lane = c (this thread), column = i
-        const long c = (long)(tile0 + t) * TILE + tid;
-        const uint32_t taddr = tmem + ((uint32_t)(32 * warp) << 16) + 64 * (t & 1);
-        float v[32];
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            tc::tmem_ld32(taddr + 32 * h, v);
-            if (c < ld) {
-#pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    const int r = 32 * h + i;
-                    const int grow = (r < BJ_B) ? bi * BJ_B + r : bj * BJ_B + (r - BJ_B);
-                    mt.X[(long)grow * ld + c] = v[i];
-                }
-            }
-        }
-    };
-    for (int t = 0; t < ntiles; ++t) {
-        if (t > 0) tc::mbar_wait(&mbar[(t - 1) & 1], (uint32_t)(((t - 1) >> 1) & 1));   // MMA(t-1) done: smem A free, D(t-1) ready
-#pragma unroll
-        for (int kq = 0; kq < BJ_M / 4; ++kq) {
-            float4 hi, lo;
-            tc::split_tf32(make_float4(x[4 * kq], x[4 * kq + 1], x[4 * kq + 2], x[4 * kq + 3]), hi, lo);
-            *reinterpret_cast<float4*>(a_hi + aoff + kq * U_LBO_A) = hi;
-            *reinterpret_cast<float4*>(a_lo + aoff + kq * U_LBO_A) = lo;
-        }
-        tc::fence_async_smem();
-        tc::tc_fence_before();
-        __syncthreads();
-        if (tid == 0) {
-            tc::tc_fence_after();
-            constexpr uint32_t idesc = tc::idesc_tf32(128, 64, 0, 0);
-            const uint32_t ah = tc::smem_u32(a_hi), al = tc::smem_u32(a_lo);
-            const uint32_t bh = tc::smem_u32(b_hi), bl = tc::smem_u32(b_lo);
-            const uint32_t d = tmem + 64 * (t & 1);
-#pragma unroll
-            for (int pass = 0; pass < 3; ++pass) {
-                const uint32_t ab = pass == 1 ? al : ah;
-                const uint32_t bb = pass == 2 ? bl : bh;
-#pragma unroll
-                for (int j = 0; j < BJ_M / 8; ++j) {
-                    const uint64_t ad = tc::smem_desc(ab + 2 * j * U_LBO_A, U_LBO_A, U_SBO);
-                    const uint64_t bd = tc::smem_desc(bb + 2 * j * U_LBO_B, U_LBO_B, U_SBO);
-                    tc::umma_tf32(d, ad, bd, idesc, !(pass == 0 && j == 0));
-                }
-            }
-            tc::umma_commit(&mbar[t & 1]);
-        }
-        if (t + 1 < ntiles) load_tile(t + 1);
-        if (t > 0) { tc::tc_fence_after(); epilogue(t - 1); }
-    }
-    tc::mbar_wait(&mbar[(ntiles - 1) & 1], (uint32_t)(((ntiles - 1) >> 1) & 1));
-    tc::tc_fence_after();
-    epilogue(ntiles - 1);
-    tc::tc_fence_before();
-    __syncthreads();
-    if (warp == 0) tc::tmem_dealloc<128>(tmem);
+    tcg::teardown(c);
 }
 
-// inner eigenproblem: sum the H partials (symmetrised), cyclic two-sided Jacobi sweeps on the
-// 64x64 block in shared memory, emit the accumulated rotations U.  grid total_pairs, 512 threads.
-// Fully unrolled, branch-free rotation application (skipped pairs carry c = 1, s = 0), one
-// float4 {c, s, p, q} per pair: ~1k cycles per round instead of ~7k for the generic routine.
-constexpr int SOLVE_THREADS = 512;
+// (2) inner eigenproblem: fixed-order sum of the H partials, symmetrise, one cyclic two-sided Jacobi
+// sweep of the 128x128 block in shared memory, emit the accumulated rotations U.  grid total_pairs.
+// Element pairs inside one 64-row block meet in EVERY round of the outer sweep, pairs across the two
+// blocks meet only here: bipartite 64-round tournament {(i, 64 + (i + r) % 64)} normally, the full
+// 127-round tournament in the first round(s) of each outer sweep.  Rotation application is fully
+// unrolled and branch-free (skipped pairs carry c = 1, s = 0), one float4 {c, s, p, q} per pair.
+constexpr int SOLVE_THREADS = 1024;
+constexpr int SOLVE_P = BJ_M + 1;
+constexpr int SOLVE_SMEM = 2 * BJ_M * SOLVE_P * (int)sizeof(float);
 __global__ void __launch_bounds__(SOLVE_THREADS)
 bj_solve_kernel(const BjMat* mats, const int* pair_mat, BjState* state, int round,
                 const float* __restrict__ partial, const long* partial_off,
                 float* __restrict__ ubuf, int inner_sweeps, int full_inner) {
-    constexpr int M = BJ_M, P = BJ_M + 1, HALF = BJ_M / 2, MM1 = BJ_M - 1;
-    constexpr int PPT = HALF / (SOLVE_THREADS / M);          // pairs per thread per phase (4)
-    __shared__ float S[M * P];
-    __shared__ float U[M * P];
+    constexpr int M = BJ_M, P = SOLVE_P, HALF = BJ_M / 2, MM1 = BJ_M - 1;
+    constexpr int GROUPS = SOLVE_THREADS / M;                // 8
+    constexpr int PPT = HALF / GROUPS;                       // pairs per thread per phase (8)
+    extern __shared__ float sm_f[];
+    float* S = sm_f;
+    float* U = sm_f + M * P;
     __shared__ float4 rot[HALF];
     __shared__ float red[SOLVE_THREADS / 32];
     const int mi = pair_mat[blockIdx.x];
@@ -592,19 +378,19 @@ bj_solve_kernel(const BjMat* mats, const int* pair_mat, BjState* state, int roun
     const int tid = threadIdx.x;
     const float* src = partial + partial_off[mi] +
                        (long)(blockIdx.x - mt.pair_begin) * mt.ksplit * (M * M);
-    // sum the split-K partials: float4 loads, 6 independent accumulators in flight (fixed order => deterministic)
+    // sum the split-K partials: float4 loads, 3 independent accumulators in flight (fixed order => deterministic)
     {
         const float4* src4 = reinterpret_cast<const float4*>(src);
 #pragma unroll
         for (int h = 0; h < (M * M / 4) / SOLVE_THREADS; ++h) {
             const int e4 = tid + h * SOLVE_THREADS;
-            float4 acc[6];
+            float4 acc[3];
 #pragma unroll
-            for (int u = 0; u < 6; ++u) acc[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int u = 0; u < 3; ++u) acc[u] = make_float4(0.f, 0.f, 0.f, 0.f);
             int z = 0;
-            for (; z + 6 <= mt.ksplit; z += 6) {
+            for (; z + 3 <= mt.ksplit; z += 3) {
 #pragma unroll
-                for (int u = 0; u < 6; ++u) {
+                for (int u = 0; u < 3; ++u) {
                     const float4 t = __ldg(src4 + (long)(z + u) * (M * M / 4) + e4);
                     acc[u].x += t.x; acc[u].y += t.y; acc[u].z += t.z; acc[u].w += t.w;
                 }
@@ -613,12 +399,11 @@ bj_solve_kernel(const BjMat* mats, const int* pair_mat, BjState* state, int roun
                 const float4 t = __ldg(src4 + (long)z * (M * M / 4) + e4);
                 acc[0].x += t.x; acc[0].y += t.y; acc[0].z += t.z; acc[0].w += t.w;
             }
-            const float vx = ((acc[0].x + acc[1].x) + (acc[2].x + acc[3].x)) + (acc[4].x + acc[5].x);
-            const float vy = ((acc[0].y + acc[1].y) + (acc[2].y + acc[3].y)) + (acc[4].y + acc[5].y);
-            const float vz = ((acc[0].z + acc[1].z) + (acc[2].z + acc[3].z)) + (acc[4].z + acc[5].z);
-            const float vw = ((acc[0].w + acc[1].w) + (acc[2].w + acc[3].w)) + (acc[4].w + acc[5].w);
             const int i = (e4 * 4) / M, j = (e4 * 4) - i * M;
-            U[i * P + j] = vx; U[i * P + j + 1] = vy; U[i * P + j + 2] = vz; U[i * P + j + 3] = vw;   // U = raw H for now
+            U[i * P + j] = (acc[0].x + acc[1].x) + acc[2].x;          // U = raw H for now
+            U[i * P + j + 1] = (acc[0].y + acc[1].y) + acc[2].y;
+            U[i * P + j + 2] = (acc[0].z + acc[1].z) + acc[2].z;
+            U[i * P + j + 3] = (acc[0].w + acc[1].w) + acc[2].w;
         }
     }
     __syncthreads();
@@ -643,10 +428,7 @@ bj_solve_kernel(const BjMat* mats, const int* pair_mat, BjState* state, int roun
         if (t > 0.f) atomicAdd(&state[mi].off2, 2.f * t);
     }
     const float abs_thr = 5e-8f * __int_as_float(state[mi].scale_bits);
-    const int row = tid & (M - 1), grp = tid >> 6;            // grp in [0, 8)
-    // Element pairs inside one 32-row block meet in EVERY round of the outer sweep, pairs across the
-    // two blocks meet only here.  So: full 63-round tournament at the first round of each outer sweep
-    // (or when full_inner is forced), otherwise just the 32 bipartite rounds {(i, 32 + (i + r) % 32)}.
+    const int row = tid & (M - 1), grp = tid / M;            // grp in [0, 8)
     // (with an odd block count one block idles per round: two leading full rounds cover every block)
     const bool full = full_inner || (round % (mt.p - 1)) < ((mt.nblk & 1) ? 2 : 1);
     const int nrounds = full ? MM1 : BJ_B;
@@ -684,7 +466,7 @@ bj_solve_kernel(const BjMat* mats, const int* pair_mat, BjState* state, int roun
                 float4 rp[PPT];
                 float sp[PPT], sq[PPT], up[PPT], uq[PPT];
 #pragma unroll
-                for (int u = 0; u < PPT; ++u) rp[u] = rot[grp + 8 * u];
+                for (int u = 0; u < PPT; ++u) rp[u] = rot[grp + GROUPS * u];
 #pragma unroll
                 for (int u = 0; u < PPT; ++u) {
                     const int p = __float_as_int(rp[u].z), q = __float_as_int(rp[u].w);
@@ -707,7 +489,7 @@ bj_solve_kernel(const BjMat* mats, const int* pair_mat, BjState* state, int roun
                 float4 rp[PPT];
                 float sp[PPT], sq[PPT];
 #pragma unroll
-                for (int u = 0; u < PPT; ++u) rp[u] = rot[grp + 8 * u];
+                for (int u = 0; u < PPT; ++u) rp[u] = rot[grp + GROUPS * u];
 #pragma unroll
                 for (int u = 0; u < PPT; ++u) {
                     const int p = __float_as_int(rp[u].z), q = __float_as_int(rp[u].w);
@@ -732,64 +514,6 @@ bj_solve_kernel(const BjMat* mats, const int* pair_mat, BjState* state, int roun
     for (int e = tid; e < M * M; e += SOLVE_THREADS) {
         const int i = e / M, j = e - i * M;
         dst[e] = U[i * P + j];
-    }
-}
-
-// rows <- U^T rows for the 64 rows of a pair, 128 columns per CTA.  grid (max col tiles, total_pairs)
-__global__ void __launch_bounds__(256)
-bj_update_kernel(const BjMat* mats, const int* pair_mat, const BjState* state, int round,
-                 const float* __restrict__ ubuf) {
-    extern __shared__ float smem[];
-    float (*us)[BJ_M] = reinterpret_cast<float (*)[BJ_M]>(smem);                 // [k][i]
-    float (*xs)[TILE] = reinterpret_cast<float (*)[TILE]>(smem + BJ_M * BJ_M);   // [k][c]
-    const int mi = pair_mat[blockIdx.y];
-    const BjMat mt = mats[mi];
-    const long ld = 2L * mt.n_pad;
-    const int c0 = blockIdx.x * TILE;
-    if (state[mi].converged || c0 >= ld) return;
-    int bi, bj;
-    if (!bj_pair_blocks(mt, blockIdx.y - mt.pair_begin, round, bi, bj)) return;
-    const int tid = threadIdx.x;
-    const float* usrc = ubuf + (long)blockIdx.y * (BJ_M * BJ_M);
-    for (int e = tid; e < BJ_M * BJ_M / 4; e += 256)
-        reinterpret_cast<float4*>(smem)[e] = reinterpret_cast<const float4*>(usrc)[e];
-    // X tile: 64 rows x 128 cols, float4 per thread (ld and c0 are multiples of 4)
-    for (int e = tid; e < BJ_M * TILE / 4; e += 256) {
-        const int r = e / (TILE / 4), c4 = e - r * (TILE / 4);
-        const int grow = (r < BJ_B) ? bi * BJ_B + r : bj * BJ_B + (r - BJ_B);
-        const int c = c0 + c4 * 4;
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (c < ld) v = *reinterpret_cast<const float4*>(mt.X + (long)grow * ld + c);
-        *reinterpret_cast<float4*>(&xs[r][c4 * 4]) = v;
-    }
-    __syncthreads();
-    const int tx = tid & 15, ty = tid >> 4;          // ty: 4 output rows, tx: 8 output cols
-    float acc[4][8];
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
-#pragma unroll 8
-    for (int k = 0; k < BJ_M; ++k) {
-        const float4 a = *reinterpret_cast<const float4*>(&us[k][ty * 4]);
-        const float4 b0 = *reinterpret_cast<const float4*>(&xs[k][tx * 4]);
-        const float4 b1 = *reinterpret_cast<const float4*>(&xs[k][64 + tx * 4]);
-        const float av[4] = {a.x, a.y, a.z, a.w};
-        const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-#pragma unroll
-            for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
-    }
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const int r = ty * 4 + i;
-        const int grow = (r < BJ_B) ? bi * BJ_B + r : bj * BJ_B + (r - BJ_B);
-        float* dst = mt.X + (long)grow * ld + c0;
-        if (c0 + tx * 4 < ld)
-            *reinterpret_cast<float4*>(dst + tx * 4) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
-        if (c0 + 64 + tx * 4 < ld)
-            *reinterpret_cast<float4*>(dst + 64 + tx * 4) = make_float4(acc[i][4], acc[i][5], acc[i][6], acc[i][7]);
     }
 }
 
@@ -1092,8 +816,6 @@ extern "C" int kfacb_eigh_batched(const int32_t* n, int32_t count,
     bj_init_kernel<<<dim3(4 * sm_count(), nb), 256, 0, st>>>(dm, dstate);
     KFACB_CHECK_LAUNCH();
 
-    const size_t upd_smem = (size_t)(BJ_M * BJ_M + BJ_M * TILE) * sizeof(float);
-    KFACB_CHECK_CUDA(cudaFuncSetAttribute(bj_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)upd_smem));
     const int col_tiles = cdiv(pl.max_ld, TILE);
     constexpr int CH = 24;            // rounds per progress chunk (host look-ahead = 2 chunks)
     cudaEvent_t ev[2];
@@ -1101,29 +823,19 @@ extern "C" int kfacb_eigh_batched(const int32_t* n, int32_t count,
     KFACB_CHECK_CUDA(cudaEventCreateWithFlags(&ev[1], cudaEventDisableTiming));
     int rc = KFACB_OK;
     const int inner_sweeps = env_int("KFACB_INNER_SWEEPS", BJ_INNER_SWEEPS);   // tuning knobs
-    const bool use_tc = env_int("KFACB_JACOBI_SIMT", 0) == 0;                  // 1 = fp32 SIMT GEMMs (debug / A-B)
-    const int full_inner = env_int("KFACB_FULL_INNER", 0);                     // 1 = 63-round inner tournament every visit
-    const int upd_g = max(1, env_int("KFACB_UPD_TILES", 4));
-    const int upd_rev = env_int("KFACB_UPD_REVERSE", 1);                   // 128-column tiles per update CTA
-    if (use_tc) {
-        KFACB_CHECK_CUDA(cudaFuncSetAttribute(bj_h_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, H_SMEM));
-        KFACB_CHECK_CUDA(cudaFuncSetAttribute(bj_update_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, U_SMEM));
-    }
+    const int full_inner = env_int("KFACB_FULL_INNER", 0);                     // 1 = full inner tournament every visit
     const int max_sweeps = env_int("KFACB_MAX_SWEEPS", BJ_MAX_SWEEPS);
+    KFACB_CHECK_CUDA(cudaFuncSetAttribute(bj_h_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tcg::SMEM));
+    KFACB_CHECK_CUDA(cudaFuncSetAttribute(bj_update_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tcg::SMEM));
+    KFACB_CHECK_CUDA(cudaFuncSetAttribute(bj_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SOLVE_SMEM));
     for (int r = 0; r < pl.max_rounds; ++r) {
         if (r % CH == 0 && r >= 2 * CH) {
             if (cudaEventSynchronize(ev[(r / CH) & 1]) != cudaSuccess) { rc = KFACB_ERR_CUDA; set_error("event sync failed"); break; }
             if (*(volatile int*)h_active == 0) break;
         }
-        if (use_tc)
-            bj_h_tc_kernel<<<dim3(pl.total_pairs, pl.max_ksplit), TC_THREADS, H_SMEM, st>>>(dm, dpm, dstate, r, partial, dpoff);
-        else
-            bj_gram_kernel<<<dim3(pl.total_pairs, pl.max_ksplit), 256, 0, st>>>(dm, dpm, dstate, r, partial, dpoff);
-        bj_solve_kernel<<<pl.total_pairs, SOLVE_THREADS, 0, st>>>(dm, dpm, dstate, r, partial, dpoff, ubuf, inner_sweeps, full_inner);
-        if (use_tc)
-            bj_update_tc_kernel<<<dim3(cdiv(col_tiles, upd_g), pl.total_pairs), TC_THREADS, U_SMEM, st>>>(dm, dpm, dstate, r, ubuf, upd_g, upd_rev);
-        else
-            bj_update_kernel<<<dim3(col_tiles, pl.total_pairs), 256, upd_smem, st>>>(dm, dpm, dstate, r, ubuf);
+        bj_h_tc_kernel<<<dim3(pl.total_pairs, pl.max_ksplit), tcg::THREADS, tcg::SMEM, st>>>(dm, dpm, dstate, r, partial, dpoff);
+        bj_solve_kernel<<<pl.total_pairs, SOLVE_THREADS, SOLVE_SMEM, st>>>(dm, dpm, dstate, r, partial, dpoff, ubuf, inner_sweeps, full_inner);
+        bj_update_tc_kernel<<<dim3(col_tiles, pl.total_pairs), tcg::THREADS, tcg::SMEM, st>>>(dm, dpm, dstate, r, ubuf);
         bool boundary = false;
         for (int k = 0; k < nb && !boundary; ++k) boundary = ((r + 1) % (hm[k].p - 1)) == 0;
         if (boundary) { bj_check_kernel<<<1, 256, 0, st>>>(dm, dstate, nb, r, max_sweeps, d_active); count_launch(1); }
