@@ -1,0 +1,75 @@
+"""BASELINE-size checks (ResNet-50 / VGG-16 layer shapes) through size-independent properties:
+the oracle cannot run a whole 4608-dim eigh in seconds on every box, so at full size we check
+trace preservation, ordering, orthogonality, reconstruction, EMA linearity and inverse * matrix = I."""
+import pytest
+import torch
+
+from oracle import kfac_oracle as orc
+from tests.oracle_engine import spec_of
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda:0'
+
+
+@pytest.fixture(scope='module')
+def eng():
+    from kfac_pytorch_b200.native import NativeEngine
+    return NativeEngine(torch.device(DEV))
+
+
+def _kfac_like_factor(n, rows, gen):
+    x = torch.randn(rows, n, device=DEV, generator=gen)
+    return (0.05 * torch.eye(n, device=DEV) + 0.95 * (x.t() @ x) / rows).contiguous()
+
+
+@pytest.mark.parametrize('n,rows', [(2304, 6272), (4608, 1568)])
+def test_eigh_resnet50_factor_sizes(eng, n, rows):
+    gen = torch.Generator(device=DEV).manual_seed(n)
+    A = _kfac_like_factor(n, rows, gen)
+    Q = torch.empty_like(A); d = torch.empty(n, device=DEV)
+    sw = torch.zeros(1, dtype=torch.int32, device=DEV)
+    eng.eigh([A], [Q], [d], 1e-10, sw)
+    A64, Q64, d64 = A.double(), Q.double(), d.double()
+    assert torch.all(d64[1:] >= d64[:-1])
+    assert abs(d64.sum().item() - A64.trace().item()) <= 2e-6 * A64.trace().item()      # trace preserved
+    assert (Q64.t() @ Q64 - torch.eye(n, device=DEV, dtype=torch.float64)).abs().max().item() < 1e-5
+    rec = (Q64 * d64) @ Q64.t()
+    assert (rec - A64).norm().item() <= 1e-4 * A64.norm().item()
+    if n == 4608:       # rank(x^T x) = 1568 < n: the 0.05 cluster of the identity part must come out flat
+        assert (d64[: n - rows] - 0.05).abs().max().item() < 2e-6
+    assert 1 <= int(sw.item()) <= 16
+
+
+def test_factor_resnet50_conv3x3_full_size_vs_oracle(eng):
+    """conv 64->64 3x3 pad 1 at 56x56, batch 32: rows = 100352, dA = 576 (tall-skinny, split-K)."""
+    from kfac_pytorch_b200.preconditioner import _full_desc
+    gen = torch.Generator().manual_seed(3)
+    m = torch.nn.Conv2d(64, 64, 3, padding=1, bias=False)
+    a = torch.randn(32, 64, 56, 56, generator=gen)
+    g = torch.randn(32, 64, 56, 56, generator=gen) / 32
+    d = _full_desc(m, a, g)
+    A = torch.empty(576, 576, device=DEV); G = torch.empty(64, 64, device=DEV)
+    eng.factor_update([d], [a.to(DEV)], [g.to(DEV)], [A], [G], 0.95, True)
+    spec = spec_of(d)
+    refA = orc.running_average(orc.factor_A(a, spec).double(), torch.eye(576, dtype=torch.float64), 0.95)
+    refG = orc.running_average(orc.factor_G(g, spec).double(), torch.eye(64, dtype=torch.float64), 0.95)
+    assert ((A.double().cpu() - refA).norm() / refA.norm()).item() < 1e-5
+    assert ((G.double().cpu() - refG).norm() / refG.norm()).item() < 1e-5
+    # EMA linearity: a second update with the same batch moves the factor by 0.05*(old - new) exactly
+    A2 = A.clone(); G2 = G.clone()
+    eng.factor_update([d], [a.to(DEV)], [g.to(DEV)], [A2], [G2], 0.95, False)
+    newA = (refA - 0.05 * torch.eye(576, dtype=torch.float64)) / 0.95
+    assert ((A2.double().cpu() - (0.05 * refA + 0.95 * newA)).norm() / refA.norm()).item() < 1e-5
+
+
+def test_inverse_vgg16_factor_size(eng):
+    n = 2305
+    gen = torch.Generator(device=DEV).manual_seed(7)
+    A = _kfac_like_factor(n, 8192, gen); G = _kfac_like_factor(256, 8192, gen) * 1e-3
+    A0 = A.clone()
+    iA = torch.empty_like(A); iG = torch.empty_like(G)
+    eng.pi_damped_inverse([A], [G], [iA], [iG], 0.03)
+    assert not torch.equal(A, A0)                       # damping persisted in place
+    eye = torch.eye(n, device=DEV, dtype=torch.float64)
+    assert ((iA.double() @ A.double()) - eye).abs().max().item() < 5e-4
+    assert torch.equal(iA, iA.t())
