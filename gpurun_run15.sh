@@ -1,13 +1,11 @@
 mkdir -p gpurun_out; rm -f gpurun_out/probe.log
 timeout 1500 python -m pytest tests -m gpu -q --timeout 900 > gpurun_out/test_all.log 2>&1; echo "tests rc=$?"
-tail -6 gpurun_out/test_all.log
+tail -5 gpurun_out/test_all.log
 P="timeout 300 python tools/eigh_probe.py"
-$P 785 512 1152 >> gpurun_out/probe.log 2>&1
-PROBE_GRADED=1 $P 513 1000 >> gpurun_out/probe.log 2>&1
 $P 4608 >> gpurun_out/probe.log 2>&1
 $P 4608 4608 4608 2304 2304 2048 2048 1152 1152 1024 1024 >> gpurun_out/probe.log 2>&1
 grep -E "^env|^  n=|Error|error" gpurun_out/probe.log
-KFACB_MAX_SWEEPS=1 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 100 -c 200 --csv --log-file gpurun_out/launches_eigh4608.csv python tools/eigh_probe.py 4608 > gpurun_out/ncu_probe.log 2>&1
+KFACB_MAX_SWEEPS=1 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 100 -c 120 --csv --log-file gpurun_out/launches_eigh4608.csv python tools/eigh_probe.py 4608 > gpurun_out/ncu_probe.log 2>&1
 python - <<'PY'
 import csv, collections
 rows=list(csv.reader(open('gpurun_out/launches_eigh4608.csv')))
@@ -18,7 +16,7 @@ for r in rows[hdr+1:]:
     if len(r)>vi:
         try: agg[r[ki][:60]].append(float(r[vi].replace(',','')))
         except: pass
-for k,v in sorted(agg.items(), key=lambda kv:-sum(kv[1])):
+for k,v in sorted(agg.items(), key=lambda kv:-sum(kv[1]))[:5]:
     print('%-62s n=%4d mean=%9.1f us total=%9.1f ms'%(k,len(v),sum(v)/len(v)/1e3,sum(v)/1e6))
 PY
 timeout 900 python bench.py --steps 3 --warmup 1 --no-cpu-baseline > gpurun_out/bench_r50.log 2>&1; echo "bench rc=$?"

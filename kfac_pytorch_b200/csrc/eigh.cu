@@ -461,6 +461,41 @@ bj_solve_kernel(const BjMat* mats, const int* pair_mat, BjState* state, int roun
                 rot[tid] = make_float4(c, sn, __int_as_float(p), __int_as_float(q));
             }
             __syncthreads();
+            if (!full) {
+                // Bipartite round: pair k = (k, 64 + (k + r) % 64).  S' = J^T S J decomposes into independent 2x2
+                // blocks indexed by (pair a, pair b): one thread loads the 4 entries, applies the right rotation
+                // (pair b) and the left rotation (pair a) in registers and stores them -- each element of S is
+                // read and written ONCE per round (the separate column/row passes touch it twice), and there
+                // is no barrier between the S and U updates.  Lanes walk b: conflict-free (pitch 129).
+                const int b = tid & (HALF - 1);
+                const float4 rb = rot[b];
+                const int qb = __float_as_int(rb.w);
+#pragma unroll
+                for (int i = 0; i < HALF / (SOLVE_THREADS / HALF); ++i) {
+                    const int a = (tid >> 6) + (SOLVE_THREADS / HALF) * i;
+                    const float4 ra = rot[a];
+                    const int qa = __float_as_int(ra.w);
+                    const float x11 = S[a * P + b], x12 = S[a * P + qb], x21 = S[qa * P + b], x22 = S[qa * P + qb];
+                    const float y11 = rb.x * x11 - rb.y * x12, y12 = rb.y * x11 + rb.x * x12;
+                    const float y21 = rb.x * x21 - rb.y * x22, y22 = rb.y * x21 + rb.x * x22;
+                    float z11 = ra.x * y11 - ra.y * y21, z21 = ra.y * y11 + ra.x * y21;
+                    float z12 = ra.x * y12 - ra.y * y22, z22 = ra.y * y12 + ra.x * y22;
+                    if (a == b && ra.y != 0.f) { z12 = 0.f; z21 = 0.f; }     // the annihilated element
+                    S[a * P + b] = z11; S[a * P + qb] = z12; S[qa * P + b] = z21; S[qa * P + qb] = z22;
+                }
+                // U <- U J: rows walk the lanes, 8 pairs per thread
+#pragma unroll
+                for (int u = 0; u < PPT; ++u) {
+                    const float4 rp = rot[grp + GROUPS * u];
+                    const int pp = __float_as_int(rp.z), qq = __float_as_int(rp.w);
+                    const float up = U[row * P + pp], uq = U[row * P + qq];
+                    U[row * P + pp] = rp.x * up - rp.y * uq;
+                    U[row * P + qq] = rp.y * up + rp.x * uq;
+                }
+                __syncthreads();
+                continue;
+            }
+            // generic (full tournament) round: column pass, barrier, row pass
             // column rotations: S <- S J, U <- U J   (this thread: row `row`, pairs grp, grp+8, ...)
             {
                 float4 rp[PPT];
@@ -787,7 +822,8 @@ extern "C" int kfacb_eigh_batched(const int32_t* n, int32_t count,
             b.lam = (float*)(ws + lo); b.nrm = b.lam + b.n_pad; lo += 2 * (size_t)b.n_pad * sizeof(float);
             b.perm = (int*)(ws + po); po += (size_t)b.n_pad * sizeof(int);
             b.pair_begin = pair; b.ksplit = cdiv(b.n_pad, BJ_KCHUNK);
-            b.tol_conv = 1e-6f * (float)env_int("KFACB_CONV_TOL_E6", 100);
+            // few blocks = short sweeps and little quadratic tail: ask for more before stopping (these are cheap)
+            b.tol_conv = 1e-6f * (float)env_int("KFACB_CONV_TOL_E6", b.p >= 16 ? 100 : 20);
             hpoff[k] = partial_off;
             partial_off += (long)(b.p / 2) * b.ksplit * BJ_M * BJ_M;
             for (int q = 0; q < b.p / 2; ++q) hpm[pair++] = k;
