@@ -149,6 +149,17 @@ struct LdMnContig {
     __device__ __forceinline__ float operator()(int mn, int k) const {
         return (mn < MN && k < K) ? __ldg(p + (long)k * s_k + mn) : 0.f;
     }
+    __device__ __forceinline__ float4 quad(int mn, int k) const {
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (mn < MN) {
+            const float* q = p + (long)k * s_k + mn;
+            if (k < K) v.x = __ldg(q);
+            if (k + 1 < K) v.y = __ldg(q + s_k);
+            if (k + 2 < K) v.z = __ldg(q + 2 * s_k);
+            if (k + 3 < K) v.w = __ldg(q + 3 * s_k);
+        }
+        return v;
+    }
 };
 
 // -------------------------------------------------------------------------

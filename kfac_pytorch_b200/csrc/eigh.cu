@@ -271,6 +271,11 @@ struct LdPairRows {
         const int grow = mn < BJ_B ? row_a + mn : row_b + (mn - BJ_B);
         return __ldg(base + (long)grow * ld + k);
     }
+    __device__ __forceinline__ float4 quad(int mn, int k) const {       // rows are 256-byte aligned, k % 4 == 0
+        if (k >= kend) return make_float4(0.f, 0.f, 0.f, 0.f);
+        const int grow = mn < BJ_B ? row_a + mn : row_b + (mn - BJ_B);
+        return __ldg(reinterpret_cast<const float4*>(base + (long)grow * ld + k));
+    }
 };
 // columns of the pair's rows viewed as a (128 columns) x (128 rows-as-k) operand (column index contiguous)
 struct LdPairCols {
@@ -282,12 +287,23 @@ struct LdPairCols {
         const int grow = k < BJ_B ? row_a + k : row_b + (k - BJ_B);
         return X[(long)grow * ld + c];          // plain load: X is rewritten in place by this kernel
     }
+    __device__ __forceinline__ float4 quad(int mn, int k) const {       // a quad never straddles the two blocks
+        const long c = c0 + mn;
+        if (c >= ld) return make_float4(0.f, 0.f, 0.f, 0.f);
+        const int grow = k < BJ_B ? row_a + k : row_b + (k - BJ_B);
+        const float* p = X + (long)grow * ld + c;
+        return make_float4(p[0], p[ld], p[2 * ld], p[3 * ld]);
+    }
 };
 // U (128x128 row-major, U[k][i]) as operand B(n = i, k)
 struct LdUmat {
     static constexpr bool K_FAST = false;
     const float* U;
     __device__ __forceinline__ float operator()(int mn, int k) const { return __ldg(U + k * BJ_M + mn); }
+    __device__ __forceinline__ float4 quad(int mn, int k) const {
+        const float* p = U + k * BJ_M + mn;
+        return make_float4(__ldg(p), __ldg(p + BJ_M), __ldg(p + 2 * BJ_M), __ldg(p + 3 * BJ_M));
+    }
 };
 
 // (1) H = V_R^T A V_R = V_R W_R^T (128x128) over one k-chunk.  grid (total_pairs, max ksplit)

@@ -50,6 +50,17 @@ struct LdNCS {
         }
         return mn == ones_col ? 1.f : 0.f;
     }
+    __device__ __forceinline__ float4 quad(int mn, int k) const {       // 4 consecutive rows (b, s..s+3)
+        if (mn < C && k + 3 < K) {
+            const int b = divS.div(k), s = k - b * S;
+            if (s + 3 < S) {
+                const float* q = p + ((long)b * C + mn) * S + s;
+                if ((S & 3) == 0) return __ldg(reinterpret_cast<const float4*>(q));     // k % 4 == 0 => 16 B aligned
+                return make_float4(__ldg(q), __ldg(q + 1), __ldg(q + 2), __ldg(q + 3));
+            }
+        }
+        return make_float4((*this)(mn, k), (*this)(mn, k + 1), (*this)(mn, k + 2), (*this)(mn, k + 3));
+    }
 };
 
 // implicit im2col: X(k=(b,oh,ow), m=(c,i,j)) = x[b, c, oh*sh+i-ph, ow*sw+j-pw] (0 outside)
@@ -68,6 +79,27 @@ struct LdIm2col {
         const int ih = oh * SH + i - PH, iw = ow * SW + j - PW;
         if ((unsigned)ih >= (unsigned)H || (unsigned)iw >= (unsigned)W) return 0.f;
         return __ldg(p + (((long)b * C + c) * H + ih) * W + iw);
+    }
+    __device__ __forceinline__ float4 quad(int mn, int k) const {       // 4 consecutive output positions, one feature
+        if (mn < D && k + 3 < K) {
+            const int b = divS.div(k), s = k - b * S;
+            const int oh = divOW.div(s), ow = s - oh * OW;
+            if (ow + 3 < OW) {                                   // same output row: decode once, walk iw by SW
+                const int c = divKHW.div(mn), r = mn - c * KHW;
+                const int i = divKW.div(r), j = r - i * KW;
+                const int ih = oh * SH + i - PH;
+                if ((unsigned)ih >= (unsigned)H) return make_float4(0.f, 0.f, 0.f, 0.f);
+                const int iw = ow * SW + j - PW;
+                const float* q = p + (((long)b * C + c) * H + ih) * W;
+                float4 v;
+                v.x = (unsigned)iw < (unsigned)W ? __ldg(q + iw) : 0.f;
+                v.y = (unsigned)(iw + SW) < (unsigned)W ? __ldg(q + iw + SW) : 0.f;
+                v.z = (unsigned)(iw + 2 * SW) < (unsigned)W ? __ldg(q + iw + 2 * SW) : 0.f;
+                v.w = (unsigned)(iw + 3 * SW) < (unsigned)W ? __ldg(q + iw + 3 * SW) : 0.f;
+                return v;
+            }
+        }
+        return make_float4((*this)(mn, k), (*this)(mn, k + 1), (*this)(mn, k + 2), (*this)(mn, k + 3));
     }
 };
 

@@ -10,6 +10,8 @@
 // The accumulator is drained through shared memory so that epilogues run with lanes along n
 // (coalesced global access, conflict-free transposed reads for mirrored stores).
 #pragma once
+#include <type_traits>
+#include <utility>
 #include "common.cuh"
 #include "tc.cuh"
 
@@ -47,6 +49,22 @@ __device__ __forceinline__ void teardown(Ctx& c) {
     if ((threadIdx.x >> 5) == 0) tc::tmem_dealloc<128>(c.tmem);
 }
 
+// Loaders may provide `float4 quad(mn, k)` = elements (mn, k..k+3) with k % 4 == 0 (one address computation,
+// vector load where the memory layout allows); the generic path calls operator() four times.
+template <class L, class = void>
+struct has_quad : std::false_type {};
+template <class L>
+struct has_quad<L, std::void_t<decltype(std::declval<const L&>().quad(0, 0))>> : std::true_type {};
+
+template <class L>
+__device__ __forceinline__ float4 load_quad(const L& ld, int mn, int k) {
+    if constexpr (has_quad<L>::value) {
+        return ld.quad(mn, k);
+    } else {
+        return make_float4(ld(mn, k), ld(mn, k + 1), ld(mn, k + 2), ld(mn, k + 3));
+    }
+}
+
 template <class L>
 __device__ __forceinline__ void fetch(const L& ld, int mn0, int k0, float4 (&r)[4]) {
     const int tid = threadIdx.x;
@@ -55,9 +73,7 @@ __device__ __forceinline__ void fetch(const L& ld, int mn0, int k0, float4 (&r)[
         const int idx = tid + THREADS * i;
         int row, kq;
         if (L::K_FAST) { kq = idx & 7; row = idx >> 3; } else { row = idx & 127; kq = idx >> 7; }
-        const int k = k0 + 4 * kq;
-        r[i].x = ld(mn0 + row, k); r[i].y = ld(mn0 + row, k + 1);
-        r[i].z = ld(mn0 + row, k + 2); r[i].w = ld(mn0 + row, k + 3);
+        r[i] = load_quad(ld, mn0 + row, k0 + 4 * kq);
     }
 }
 template <class L>
