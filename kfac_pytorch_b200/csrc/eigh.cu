@@ -333,36 +333,165 @@ bj_h_tc_kernel(const BjMat* mats, const int* pair_mat, const BjState* state, int
     tcg::teardown(c);
 }
 
-// (3) rows <- U^T rows for the 128 rows of a pair (W and V halves together), 128 columns per CTA:
-//     D[c][i] = sum_k X[r_k][c] U[k][i].  grid (col tiles, total_pairs)
-__global__ void __launch_bounds__(tcg::THREADS)
+// (3) rows <- U^T rows for the 128 rows of a pair (W and V halves together):
+//     D[c][i] = sum_k X[r_k][c] U[k][i]   (M = 128 columns of X per tile, N = 128, K = 128).
+// Warp-specialised, persistent over `tiles_per_cta` consecutive 128-column tiles of one pair:
+//   * U (128x128) is split into tf32 hi/lo and staged ONCE (128 KB, K-major core-matrix layout);
+//   * warps 0-3 (producers): thread c owns column c of the tile; the 32 loads of k-slab q+2 are in
+//     flight while slab q is split + stored into one of two 32 KB operand buffers and its 12 UMMAs
+//     (3xTF32, 128x128x8) are issued; buffers are recycled through tcgen05.commit -> mbarrier;
+//   * warps 4-7 (epilogue): wait for the tile's accumulator (2 x 128 TMEM columns, double buffered),
+//     tcgen05.ld it and store the rows back in place (lanes = consecutive columns: coalesced).
+// grid (ceil(col_tiles / tiles_per_cta), total_pairs)
+constexpr int UPD_THREADS = 256;
+constexpr int UPD_LBO = (TILE / 8) * 128;                 // 2048: stride between k-quads
+constexpr int UPD_U_PART = (BJ_M / 4) * UPD_LBO;          // 65536 bytes: U hi (or lo)
+constexpr int UPD_A_PART = (32 / 4) * UPD_LBO;            // 16384 bytes: one k-slab of X hi (or lo)
+constexpr int UPD_SMEM = 2 * UPD_U_PART + 4 * UPD_A_PART; // 196608
+__global__ void __launch_bounds__(UPD_THREADS)
 bj_update_tc_kernel(const BjMat* mats, const int* pair_mat, const BjState* state, int round,
-                    const float* __restrict__ ubuf) {
+                    const float* __restrict__ ubuf, int tiles_per_cta) {
     extern __shared__ __align__(128) unsigned char dsm_raw[];
-    __shared__ __align__(8) uint64_t mbar;
+    __shared__ __align__(8) uint64_t bar_smem[2], bar_full[2], bar_empty[2];
     __shared__ uint32_t tmem_slot;
     const int pair_idx = blockIdx.y;
     const int mi = pair_mat[pair_idx];
     const BjMat mt = mats[mi];
     const long ld = 2L * mt.n_pad;
-    const long c0 = (long)blockIdx.x * TILE;
-    if (state[mi].converged || c0 >= ld) return;
+    const int tile0 = blockIdx.x * tiles_per_cta;
+    if (state[mi].converged || (long)tile0 * TILE >= ld) return;
     int bi, bj;
     if (!bj_pair_blocks(mt, pair_idx - mt.pair_begin, round, bi, bj)) return;
-    tcg::Ctx c;
-    tcg::setup(c, dsm_raw, &mbar, &tmem_slot);
-    LdPairCols la{mt.X, ld, bi * BJ_B, bj * BJ_B, c0};
-    LdUmat lb{ubuf + (long)pair_idx * (BJ_M * BJ_M)};
-    tcg::mainloop(la, lb, 0, 0, 0, BJ_M, false, c);          // the whole input tile is consumed here ...
-    const float* d = tcg::drain(c, true);
-    for (int e = threadIdx.x; e < BJ_M * TILE; e += tcg::THREADS) {   // ... before it is overwritten in place
-        const int i = e >> 7, cc = e & 127;                  // lanes along the column: coalesced stores,
-        if (c0 + cc < ld) {                                  // conflict-free transposed read of d[cc][i]
-            const int grow = i < BJ_B ? bi * BJ_B + i : bj * BJ_B + (i - BJ_B);
-            mt.X[(long)grow * ld + c0 + cc] = d[cc * tcg::DPITCH + i];
+    const int ntiles = min(tiles_per_cta, (int)((ld - (long)tile0 * TILE + TILE - 1) / TILE));
+    const int tid = threadIdx.x, warp = tid >> 5;
+    if (tid == 0) {
+        tc::mbar_init(&bar_smem[0], 1); tc::mbar_init(&bar_smem[1], 1);
+        tc::mbar_init(&bar_full[0], 1); tc::mbar_init(&bar_full[1], 1);
+        tc::mbar_init(&bar_empty[0], 128); tc::mbar_init(&bar_empty[1], 128);
+        tc::fence_mbar_init();
+    }
+    if (warp == 0) tc::tmem_alloc<256>(&tmem_slot);
+    unsigned char* u_hi = dsm_raw;
+    unsigned char* u_lo = dsm_raw + UPD_U_PART;
+    unsigned char* a_buf = dsm_raw + 2 * UPD_U_PART;          // [buffer][hi|lo] x UPD_A_PART
+    // stage U once: operand B(n = i, k) = U[k][i]; thread (i, kq) gathers 4 rows of column i (coalesced along i)
+    {
+        const float* usrc = ubuf + (long)pair_idx * (BJ_M * BJ_M);
+        const int i = tid & 127;
+        const int boff = (i & 7) * 16 + (i >> 3) * 128;
+#pragma unroll 4
+        for (int j = 0; j < (BJ_M / 4) / 2; ++j) {
+            const int kq = (tid >> 7) + 2 * j;
+            const float* src = usrc + (4 * kq) * BJ_M + i;
+            float4 u = make_float4(__ldg(src), __ldg(src + BJ_M), __ldg(src + 2 * BJ_M), __ldg(src + 3 * BJ_M));
+            float4 hi, lo;
+            tc::split_tf32(u, hi, lo);
+            *reinterpret_cast<float4*>(u_hi + boff + kq * UPD_LBO) = hi;
+            *reinterpret_cast<float4*>(u_lo + boff + kq * UPD_LBO) = lo;
         }
     }
-    tcg::teardown(c);
+    tc::fence_async_smem();
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tmem = tmem_slot;
+    const int row_a = bi * BJ_B, row_b = bj * BJ_B;
+
+    if (warp < 4) {
+        // ===================== producers: load / split / stage / issue =====================
+        const int c = tid;                                   // column of the tile owned by this thread
+        const int aoff = (c & 7) * 16 + (c >> 3) * 128;
+        const int nslab = ntiles * 4;
+        float x[2][32];                                      // two k-slabs of this column in flight
+        auto load_slab = [&](int q, float (&dst)[32]) {
+            const int t = q >> 2, s = q & 3;
+            const long col = (long)(tile0 + t) * TILE + c;
+            if (col < ld) {
+#pragma unroll
+                for (int kk = 0; kk < 32; ++kk) {
+                    const int k = 32 * s + kk;
+                    const int grow = k < BJ_B ? row_a + k : row_b + (k - BJ_B);
+                    dst[kk] = mt.X[(long)grow * ld + col];
+                }
+            } else {
+#pragma unroll
+                for (int kk = 0; kk < 32; ++kk) dst[kk] = 0.f;
+            }
+        };
+        auto stage_and_issue = [&](int q, float (&src)[32]) {
+            const int b = q & 1, u = q >> 1;
+            if (u > 0) tc::mbar_wait(&bar_smem[b], (uint32_t)((u - 1) & 1));        // buffer b free again
+            unsigned char* hi_p = a_buf + (2 * b) * UPD_A_PART;
+            unsigned char* lo_p = hi_p + UPD_A_PART;
+#pragma unroll
+            for (int kq = 0; kq < 8; ++kq) {
+                float4 hi, lo;
+                tc::split_tf32(make_float4(src[4 * kq], src[4 * kq + 1], src[4 * kq + 2], src[4 * kq + 3]), hi, lo);
+                *reinterpret_cast<float4*>(hi_p + aoff + kq * UPD_LBO) = hi;
+                *reinterpret_cast<float4*>(lo_p + aoff + kq * UPD_LBO) = lo;
+            }
+            if (q + 2 < nslab) load_slab(q + 2, src);         // refill the registers: in flight for two slabs
+            tc::fence_async_smem();
+            tc::named_bar_sync(1, 128);
+            if (tid == 0) {
+                const int t = q >> 2, s = q & 3, tb = t & 1, ut = t >> 1;
+                if (s == 0 && ut > 0) tc::mbar_wait(&bar_empty[tb], (uint32_t)((ut - 1) & 1));   // accumulator drained
+                tc::tc_fence_after();
+                constexpr uint32_t idesc = tc::idesc_tf32(128, 128, 0, 0);
+                const uint32_t ah = tc::smem_u32(hi_p), al = tc::smem_u32(lo_p);
+                const uint32_t bh = tc::smem_u32(u_hi) + 8 * s * UPD_LBO, bl = tc::smem_u32(u_lo) + 8 * s * UPD_LBO;
+                const uint32_t d = tmem + 128 * tb;
+#pragma unroll
+                for (int pass = 0; pass < 3; ++pass) {
+                    const uint32_t ab = pass == 1 ? al : ah;
+                    const uint32_t bb = pass == 2 ? bl : bh;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const uint64_t ad = tc::smem_desc(ab + 2 * j * UPD_LBO, UPD_LBO, 128);
+                        const uint64_t bd = tc::smem_desc(bb + 2 * j * UPD_LBO, UPD_LBO, 128);
+                        tc::umma_tf32(d, ad, bd, idesc, !(s == 0 && pass == 0 && j == 0));
+                    }
+                }
+                tc::umma_commit(&bar_smem[b]);
+                if (s == 3) tc::umma_commit(&bar_full[tb]);
+            }
+        };
+        load_slab(0, x[0]);
+        if (nslab > 1) load_slab(1, x[1]);
+        for (int q = 0; q < nslab; q += 2) {
+            stage_and_issue(q, x[0]);
+            if (q + 1 < nslab) stage_and_issue(q + 1, x[1]);
+        }
+    } else {
+        // ===================== epilogue: TMEM -> rows of X, in place =====================
+        const int w4 = warp & 3, lane = tid & 31;
+        const int c = 32 * w4 + lane;                        // TMEM lane = column of the tile
+        for (int t = 0; t < ntiles; ++t) {
+            const int tb = t & 1, ut = t >> 1;
+            tc::mbar_wait(&bar_full[tb], (uint32_t)(ut & 1));
+            tc::tc_fence_after();
+            const long col = (long)(tile0 + t) * TILE + c;
+            const uint32_t taddr = tmem + ((uint32_t)(32 * w4) << 16) + 128 * tb;
+            float v[32];
+#pragma unroll
+            for (int h = 0; h < 4; ++h) {
+                tc::tmem_ld32(taddr + 32 * h, v);
+                if (col < ld) {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) {
+                        const int r = 32 * h + i;
+                        const int grow = r < BJ_B ? row_a + r : row_b + (r - BJ_B);
+                        mt.X[(long)grow * ld + col] = v[i];
+                    }
+                }
+            }
+            tc::tc_fence_before();
+            tc::mbar_arrive(&bar_empty[tb]);
+        }
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tc::tmem_dealloc<256>(tmem);
 }
 
 // (2) inner eigenproblem: fixed-order sum of the H partials, symmetrise, one cyclic two-sided Jacobi
@@ -878,7 +1007,8 @@ extern "C" int kfacb_eigh_batched(const int32_t* n, int32_t count,
     const int full_inner = env_int("KFACB_FULL_INNER", 0);                     // 1 = full inner tournament every visit
     const int max_sweeps = env_int("KFACB_MAX_SWEEPS", BJ_MAX_SWEEPS);
     KFACB_CHECK_CUDA(cudaFuncSetAttribute(bj_h_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tcg::SMEM));
-    KFACB_CHECK_CUDA(cudaFuncSetAttribute(bj_update_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tcg::SMEM));
+    KFACB_CHECK_CUDA(cudaFuncSetAttribute(bj_update_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, UPD_SMEM));
+    const int upd_g = max(1, env_int("KFACB_UPD_TILES", 8));                   // 128-column tiles per update CTA
     KFACB_CHECK_CUDA(cudaFuncSetAttribute(bj_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SOLVE_SMEM));
     for (int r = 0; r < pl.max_rounds; ++r) {
         if (r % CH == 0 && r >= 2 * CH) {
@@ -887,7 +1017,7 @@ extern "C" int kfacb_eigh_batched(const int32_t* n, int32_t count,
         }
         bj_h_tc_kernel<<<dim3(pl.total_pairs, pl.max_ksplit), tcg::THREADS, tcg::SMEM, st>>>(dm, dpm, dstate, r, partial, dpoff);
         bj_solve_kernel<<<pl.total_pairs, SOLVE_THREADS, SOLVE_SMEM, st>>>(dm, dpm, dstate, r, partial, dpoff, ubuf, inner_sweeps, full_inner);
-        bj_update_tc_kernel<<<dim3(col_tiles, pl.total_pairs), tcg::THREADS, tcg::SMEM, st>>>(dm, dpm, dstate, r, ubuf);
+        bj_update_tc_kernel<<<dim3(cdiv(col_tiles, upd_g), pl.total_pairs), UPD_THREADS, UPD_SMEM, st>>>(dm, dpm, dstate, r, ubuf, upd_g);
         bool boundary = false;
         for (int k = 0; k < nb && !boundary; ++k) boundary = ((r + 1) % (hm[k].p - 1)) == 0;
         if (boundary) { bj_check_kernel<<<1, 256, 0, st>>>(dm, dstate, nb, r, max_sweeps, d_active); count_launch(1); }

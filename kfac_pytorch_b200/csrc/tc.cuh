@@ -39,6 +39,14 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         : "memory");
 }
 
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(smem_u32(bar)) : "memory");
+}
+// named barrier among a subset of the CTA's warps
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
 // ---- proxy / tcgen05 fences ----
 __device__ __forceinline__ void fence_async_smem() {          // generic-proxy STS -> visible to UMMA
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
