@@ -337,13 +337,15 @@ bj_h_tc_kernel(const BjMat* mats, const int* pair_mat, const BjState* state, int
 //     D[c][i] = sum_k X[r_k][c] U[k][i]   (M = 128 columns of X per tile, N = 128, K = 128).
 // Warp-specialised, persistent over `tiles_per_cta` consecutive 128-column tiles of one pair:
 //   * U (128x128) is split into tf32 hi/lo and staged ONCE (128 KB, K-major core-matrix layout);
-//   * warps 0-3 (producers): thread c owns column c of the tile; the 32 loads of k-slab q+2 are in
-//     flight while slab q is split + stored into one of two 32 KB operand buffers and its 12 UMMAs
-//     (3xTF32, 128x128x8) are issued; buffers are recycled through tcgen05.commit -> mbarrier;
-//   * warps 4-7 (epilogue): wait for the tile's accumulator (2 x 128 TMEM columns, double buffered),
+//   * warps 0-7 (producers): thread (c, h) owns column c / row half h of a 32-row k-slab; its 16 loads of
+//     slabs q+1..q+4 are in flight (64 KB per SM) while slab q is split + stored into one of two 32 KB
+//     operand buffers and its 12 UMMAs (3xTF32, 128x128x8) are issued; buffers are recycled through
+//     tcgen05.commit -> mbarrier;
+//   * warps 8-11 (epilogue): wait for the tile's accumulator (2 x 128 TMEM columns, double buffered),
 //     tcgen05.ld it and store the rows back in place (lanes = consecutive columns: coalesced).
 // grid (ceil(col_tiles / tiles_per_cta), total_pairs)
-constexpr int UPD_THREADS = 256;
+constexpr int UPD_PRODUCERS = 256;                       // 8 producer warps
+constexpr int UPD_THREADS = UPD_PRODUCERS + 128;         // + 4 epilogue warps
 constexpr int UPD_LBO = (TILE / 8) * 128;                 // 2048: stride between k-quads
 constexpr int UPD_U_PART = (BJ_M / 4) * UPD_LBO;          // 65536 bytes: U hi (or lo)
 constexpr int UPD_A_PART = (32 / 4) * UPD_LBO;            // 16384 bytes: one k-slab of X hi (or lo)
@@ -380,7 +382,7 @@ bj_update_tc_kernel(const BjMat* mats, const int* pair_mat, const BjState* state
         const int i = tid & 127;
         const int boff = (i & 7) * 16 + (i >> 3) * 128;
 #pragma unroll 4
-        for (int j = 0; j < (BJ_M / 4) / 2; ++j) {
+        for (int j = 0; j < (BJ_M / 4) / 2 && tid < 256; ++j) {
             const int kq = (tid >> 7) + 2 * j;
             const float* src = usrc + (4 * kq) * BJ_M + i;
             float4 u = make_float4(__ldg(src), __ldg(src + BJ_M), __ldg(src + 2 * BJ_M), __ldg(src + 3 * BJ_M));
@@ -397,49 +399,50 @@ bj_update_tc_kernel(const BjMat* mats, const int* pair_mat, const BjState* state
     const uint32_t tmem = tmem_slot;
     const int row_a = bi * BJ_B, row_b = bj * BJ_B;
 
-    if (warp < 4) {
+    if (warp < UPD_PRODUCERS / 32) {
         // ===================== producers: load / split / stage / issue =====================
-        const int c = tid;                                   // column of the tile owned by this thread
+        const int c = tid & 127, hrow = tid >> 7;            // column of the tile, half (16 rows) of each slab
         const int aoff = (c & 7) * 16 + (c >> 3) * 128;
         const int nslab = ntiles * 4;
-        float x[2][32];                                      // two k-slabs of this column in flight
-        auto load_slab = [&](int q, float (&dst)[32]) {
-            const int t = q >> 2, s = q & 3;
+        float x[4][16];                                      // four k-slabs (this thread's half) in flight
+        auto load_slab = [&](int q, float (&dst)[16]) {
+            const int t = q >> 2, sl = q & 3;
             const long col = (long)(tile0 + t) * TILE + c;
-            if (col < ld) {
+            if (q < nslab && col < ld) {
 #pragma unroll
-                for (int kk = 0; kk < 32; ++kk) {
-                    const int k = 32 * s + kk;
+                for (int kk = 0; kk < 16; ++kk) {
+                    const int k = 32 * sl + 16 * hrow + kk;
                     const int grow = k < BJ_B ? row_a + k : row_b + (k - BJ_B);
                     dst[kk] = mt.X[(long)grow * ld + col];
                 }
             } else {
 #pragma unroll
-                for (int kk = 0; kk < 32; ++kk) dst[kk] = 0.f;
+                for (int kk = 0; kk < 16; ++kk) dst[kk] = 0.f;
             }
         };
-        auto stage_and_issue = [&](int q, float (&src)[32]) {
+        auto stage_and_issue = [&](int q, float (&src)[16]) {
             const int b = q & 1, u = q >> 1;
             if (u > 0) tc::mbar_wait(&bar_smem[b], (uint32_t)((u - 1) & 1));        // buffer b free again
             unsigned char* hi_p = a_buf + (2 * b) * UPD_A_PART;
             unsigned char* lo_p = hi_p + UPD_A_PART;
 #pragma unroll
-            for (int kq = 0; kq < 8; ++kq) {
+            for (int j = 0; j < 4; ++j) {
+                const int kq = 4 * hrow + j;
                 float4 hi, lo;
-                tc::split_tf32(make_float4(src[4 * kq], src[4 * kq + 1], src[4 * kq + 2], src[4 * kq + 3]), hi, lo);
+                tc::split_tf32(make_float4(src[4 * j], src[4 * j + 1], src[4 * j + 2], src[4 * j + 3]), hi, lo);
                 *reinterpret_cast<float4*>(hi_p + aoff + kq * UPD_LBO) = hi;
                 *reinterpret_cast<float4*>(lo_p + aoff + kq * UPD_LBO) = lo;
             }
-            if (q + 2 < nslab) load_slab(q + 2, src);         // refill the registers: in flight for two slabs
+            load_slab(q + 4, src);                           // refill the registers: in flight for four slabs
             tc::fence_async_smem();
-            tc::named_bar_sync(1, 128);
+            tc::named_bar_sync(1, UPD_PRODUCERS);
             if (tid == 0) {
-                const int t = q >> 2, s = q & 3, tb = t & 1, ut = t >> 1;
-                if (s == 0 && ut > 0) tc::mbar_wait(&bar_empty[tb], (uint32_t)((ut - 1) & 1));   // accumulator drained
+                const int t = q >> 2, sl = q & 3, tb = t & 1, ut = t >> 1;
+                if (sl == 0 && ut > 0) tc::mbar_wait(&bar_empty[tb], (uint32_t)((ut - 1) & 1));   // accumulator drained
                 tc::tc_fence_after();
                 constexpr uint32_t idesc = tc::idesc_tf32(128, 128, 0, 0);
                 const uint32_t ah = tc::smem_u32(hi_p), al = tc::smem_u32(lo_p);
-                const uint32_t bh = tc::smem_u32(u_hi) + 8 * s * UPD_LBO, bl = tc::smem_u32(u_lo) + 8 * s * UPD_LBO;
+                const uint32_t bh = tc::smem_u32(u_hi) + 8 * sl * UPD_LBO, bl = tc::smem_u32(u_lo) + 8 * sl * UPD_LBO;
                 const uint32_t d = tmem + 128 * tb;
 #pragma unroll
                 for (int pass = 0; pass < 3; ++pass) {
@@ -449,18 +452,19 @@ bj_update_tc_kernel(const BjMat* mats, const int* pair_mat, const BjState* state
                     for (int j = 0; j < 4; ++j) {
                         const uint64_t ad = tc::smem_desc(ab + 2 * j * UPD_LBO, UPD_LBO, 128);
                         const uint64_t bd = tc::smem_desc(bb + 2 * j * UPD_LBO, UPD_LBO, 128);
-                        tc::umma_tf32(d, ad, bd, idesc, !(s == 0 && pass == 0 && j == 0));
+                        tc::umma_tf32(d, ad, bd, idesc, !(sl == 0 && pass == 0 && j == 0));
                     }
                 }
                 tc::umma_commit(&bar_smem[b]);
-                if (s == 3) tc::umma_commit(&bar_full[tb]);
+                if (sl == 3) tc::umma_commit(&bar_full[tb]);
             }
         };
-        load_slab(0, x[0]);
-        if (nslab > 1) load_slab(1, x[1]);
-        for (int q = 0; q < nslab; q += 2) {
+        load_slab(0, x[0]); load_slab(1, x[1]); load_slab(2, x[2]); load_slab(3, x[3]);
+        for (int q = 0; q < nslab; q += 4) {                 // nslab is a multiple of 4
             stage_and_issue(q, x[0]);
-            if (q + 1 < nslab) stage_and_issue(q + 1, x[1]);
+            stage_and_issue(q + 1, x[1]);
+            stage_and_issue(q + 2, x[2]);
+            stage_and_issue(q + 3, x[3]);
         }
     } else {
         // ===================== epilogue: TMEM -> rows of X, in place =====================
@@ -1003,6 +1007,11 @@ extern "C" int kfacb_eigh_batched(const int32_t* n, int32_t count,
     KFACB_CHECK_CUDA(cudaEventCreateWithFlags(&ev[0], cudaEventDisableTiming));
     KFACB_CHECK_CUDA(cudaEventCreateWithFlags(&ev[1], cudaEventDisableTiming));
     int rc = KFACB_OK;
+    const bool prof = env_int("KFACB_PROFILE", 0) != 0;
+    cudaEvent_t pev[4];
+    double ptime[3] = {0, 0, 0};
+    int prounds = 0;
+    if (prof) for (int k = 0; k < 4; ++k) cudaEventCreate(&pev[k]);
     const int inner_sweeps = env_int("KFACB_INNER_SWEEPS", BJ_INNER_SWEEPS);   // tuning knobs
     const int full_inner = env_int("KFACB_FULL_INNER", 0);                     // 1 = full inner tournament every visit
     const int max_sweeps = env_int("KFACB_MAX_SWEEPS", BJ_MAX_SWEEPS);
@@ -1015,9 +1024,19 @@ extern "C" int kfacb_eigh_batched(const int32_t* n, int32_t count,
             if (cudaEventSynchronize(ev[(r / CH) & 1]) != cudaSuccess) { rc = KFACB_ERR_CUDA; set_error("event sync failed"); break; }
             if (*(volatile int*)h_active == 0) break;
         }
+        if (prof) cudaEventRecord(pev[0], st);
         bj_h_tc_kernel<<<dim3(pl.total_pairs, pl.max_ksplit), tcg::THREADS, tcg::SMEM, st>>>(dm, dpm, dstate, r, partial, dpoff);
+        if (prof) cudaEventRecord(pev[1], st);
         bj_solve_kernel<<<pl.total_pairs, SOLVE_THREADS, SOLVE_SMEM, st>>>(dm, dpm, dstate, r, partial, dpoff, ubuf, inner_sweeps, full_inner);
+        if (prof) cudaEventRecord(pev[2], st);
         bj_update_tc_kernel<<<dim3(cdiv(col_tiles, upd_g), pl.total_pairs), UPD_THREADS, UPD_SMEM, st>>>(dm, dpm, dstate, r, ubuf, upd_g);
+        if (prof) {          // KFACB_PROFILE=1: per-kernel time of every round (debug only: synchronises each round)
+            cudaEventRecord(pev[3], st);
+            cudaEventSynchronize(pev[3]);
+            float t;
+            for (int k = 0; k < 3; ++k) { cudaEventElapsedTime(&t, pev[k], pev[k + 1]); ptime[k] += t; }
+            ++prounds;
+        }
         bool boundary = false;
         for (int k = 0; k < nb && !boundary; ++k) boundary = ((r + 1) % (hm[k].p - 1)) == 0;
         if (boundary) { bj_check_kernel<<<1, 256, 0, st>>>(dm, dstate, nb, r, max_sweeps, d_active); count_launch(1); }
@@ -1026,6 +1045,11 @@ extern "C" int kfacb_eigh_batched(const int32_t* n, int32_t count,
         if (r % CH == CH - 1) cudaEventRecord(ev[(r / CH) & 1], st);
     }
     cudaEventDestroy(ev[0]); cudaEventDestroy(ev[1]);
+    if (prof) {
+        fprintf(stderr, "[kfacb eigh profile] matrices=%d pairs=%d rounds=%d  H %.1f ms  solve %.1f ms  update %.1f ms\n",
+                nb, pl.total_pairs, prounds, ptime[0], ptime[1], ptime[2]);
+        for (int k = 0; k < 4; ++k) cudaEventDestroy(pev[k]);
+    }
     if (rc) return rc;
 
     // one Newton-Schulz step removes the orthogonality drift of ~1e3 accumulated fp32 rotations
