@@ -306,28 +306,31 @@ struct LdUmat {
     }
 };
 
-// (1) H = V_R^T A V_R = V_R W_R^T (128x128) over one k-chunk.  grid (total_pairs, max ksplit)
+// (1) H = V_R^T A V_R = V_R W_R^T (128x128) over one k-chunk.  grid (max ksplit, total_pairs)
 __global__ void __launch_bounds__(tcg::THREADS)
 bj_h_tc_kernel(const BjMat* mats, const int* pair_mat, const BjState* state, int round,
                float* __restrict__ partial, const long* partial_off) {
     extern __shared__ __align__(128) unsigned char dsm_raw[];
     __shared__ __align__(8) uint64_t mbar;
     __shared__ uint32_t tmem_slot;
-    const int mi = pair_mat[blockIdx.x];
+    // grid (max ksplit, total_pairs): the k-chunks of one pair are neighbours in launch order, so the CTAs
+    // resident together stream adjacent 2 KB segments of the same 128 rows (DRAM page locality)
+    const int pair_idx = blockIdx.y, zchunk = blockIdx.x;
+    const int mi = pair_mat[pair_idx];
     const BjMat mt = mats[mi];
-    if (state[mi].converged || (int)blockIdx.y >= mt.ksplit) return;
+    if (state[mi].converged || zchunk >= mt.ksplit) return;
     int bi, bj;
-    if (!bj_pair_blocks(mt, blockIdx.x - mt.pair_begin, round, bi, bj)) return;
+    if (!bj_pair_blocks(mt, pair_idx - mt.pair_begin, round, bi, bj)) return;
     tcg::Ctx c;
     tcg::setup(c, dsm_raw, &mbar, &tmem_slot);
     const long ld = 2L * mt.n_pad;
-    const int kbeg = blockIdx.y * BJ_KCHUNK, kend = min(mt.n_pad, kbeg + BJ_KCHUNK);
+    const int kbeg = zchunk * BJ_KCHUNK, kend = min(mt.n_pad, kbeg + BJ_KCHUNK);
     LdPairRows lv{mt.X + mt.n_pad, ld, bi * BJ_B, bj * BJ_B, kend};      // V rows
     LdPairRows lw{mt.X, ld, bi * BJ_B, bj * BJ_B, kend};                 // W rows
     tcg::mainloop(lv, lw, 0, 0, kbeg, kend, false, c);
     const float* d = tcg::drain(c, true);
     float* dst = partial + partial_off[mi] +
-                 ((long)(blockIdx.x - mt.pair_begin) * mt.ksplit + blockIdx.y) * (BJ_M * BJ_M);
+                 ((long)(pair_idx - mt.pair_begin) * mt.ksplit + zchunk) * (BJ_M * BJ_M);
     for (int e = threadIdx.x; e < BJ_M * BJ_M; e += tcg::THREADS)
         dst[e] = d[(e >> 7) * tcg::DPITCH + (e & 127)];
     tcg::teardown(c);
@@ -1025,7 +1028,7 @@ extern "C" int kfacb_eigh_batched(const int32_t* n, int32_t count,
             if (*(volatile int*)h_active == 0) break;
         }
         if (prof) cudaEventRecord(pev[0], st);
-        bj_h_tc_kernel<<<dim3(pl.total_pairs, pl.max_ksplit), tcg::THREADS, tcg::SMEM, st>>>(dm, dpm, dstate, r, partial, dpoff);
+        bj_h_tc_kernel<<<dim3(pl.max_ksplit, pl.total_pairs), tcg::THREADS, tcg::SMEM, st>>>(dm, dpm, dstate, r, partial, dpoff);
         if (prof) cudaEventRecord(pev[1], st);
         bj_solve_kernel<<<pl.total_pairs, SOLVE_THREADS, SOLVE_SMEM, st>>>(dm, dpm, dstate, r, partial, dpoff, ubuf, inner_sweeps, full_inner);
         if (prof) cudaEventRecord(pev[2], st);

@@ -185,6 +185,8 @@ __global__ void symmetrize_kernel(float* __restrict__ W, int n) {
     }
 }
 
+constexpr int INV_STREAMS = 4;     // independent matrices are inverted concurrently on internal streams
+
 static size_t inv_scratch_bytes(int nmax) {
     // D (64x64) + C (nmax x 64)
     return align_up(GJ_NB * GJ_NB * sizeof(float), 256) + align_up((size_t)nmax * GJ_NB * sizeof(float), 256);
@@ -218,7 +220,7 @@ extern "C" size_t kfacb_spd_inverse_workspace_bytes(const int32_t* nA, const int
         if (nG[i] > nmax) nmax = nG[i];
     }
     return align_up(sizeof(DampJob) * (size_t)(count + 1), 256) +
-           align_up(sizeof(SmallInvJob) * (size_t)(2 * count + 1), 256) + inv_scratch_bytes(nmax) + 256;
+           align_up(sizeof(SmallInvJob) * (size_t)(2 * count + 1), 256) + INV_STREAMS * inv_scratch_bytes(nmax) + 256;
 }
 
 extern "C" int kfacb_pi_damped_inverse(const int32_t* nA, const int32_t* nG, int32_t count,
@@ -267,10 +269,43 @@ extern "C" int kfacb_pi_damped_inverse(const int32_t* nA, const int32_t* nG, int
         gj_small_kernel<<<ns, 256, 0, st>>>(sjobs);
         KFACB_CHECK_LAUNCH();
     }
-    for (int i = 0; i < count; ++i) {
-        if (!A[i]) continue;
-        if (nA[i] > GJ_NB) { int rc = invert_large(A[i], invA[i], nA[i], D, C, st); if (rc) return rc; }
-        if (nG[i] > GJ_NB) { int rc = invert_large(G[i], invG[i], nG[i], D, C, st); if (rc) return rc; }
+    // The ~n/64 dependent steps of one block Gauss-Jordan sweep use few SMs each: run independent matrices
+    // concurrently on INV_STREAMS internal streams (fork from / join into the caller's stream with events).
+    static cudaStream_t xs[INV_STREAMS] = {nullptr};
+    static cudaEvent_t ev_fork = nullptr, ev_join[INV_STREAMS] = {nullptr};
+    if (!ev_fork) {
+        KFACB_CHECK_CUDA(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
+        for (int k = 0; k < INV_STREAMS; ++k) {
+            KFACB_CHECK_CUDA(cudaStreamCreateWithFlags(&xs[k], cudaStreamNonBlocking));
+            KFACB_CHECK_CUDA(cudaEventCreateWithFlags(&ev_join[k], cudaEventDisableTiming));
+        }
     }
+    int nmax = 1;
+    for (int i = 0; i < count; ++i) { if (nA[i] > nmax) nmax = nA[i]; if (nG[i] > nmax) nmax = nG[i]; }
+    const size_t scratch = inv_scratch_bytes(nmax);
+    KFACB_CHECK_CUDA(cudaEventRecord(ev_fork, st));
+    for (int k = 0; k < INV_STREAMS; ++k) KFACB_CHECK_CUDA(cudaStreamWaitEvent(xs[k], ev_fork, 0));
+    int next = 0;
+    auto run = [&](const float* Msrc, float* out, int n) -> int {
+        const int k = next++ % INV_STREAMS;
+        float* Dk = (float*)((char*)D + k * scratch);
+        float* Ck = (float*)((char*)Dk + align_up(GJ_NB * GJ_NB * sizeof(float), 256));
+        return invert_large(Msrc, out, n, Dk, Ck, xs[k]);
+    };
+    // largest first: better packing of the streams
+    int rc_all = KFACB_OK;
+    for (int pass = 0; pass < 2 && !rc_all; ++pass) {
+        for (int i = 0; i < count && !rc_all; ++i) {
+            if (!A[i]) continue;
+            const bool bigA = nA[i] > 1024, bigG = nG[i] > 1024;
+            if (nA[i] > GJ_NB && (pass == 0) == bigA) rc_all = run(A[i], invA[i], nA[i]);
+            if (!rc_all && nG[i] > GJ_NB && (pass == 0) == bigG) rc_all = run(G[i], invG[i], nG[i]);
+        }
+    }
+    for (int k = 0; k < INV_STREAMS; ++k) {
+        KFACB_CHECK_CUDA(cudaEventRecord(ev_join[k], xs[k]));
+        KFACB_CHECK_CUDA(cudaStreamWaitEvent(st, ev_join[k], 0));
+    }
+    if (rc_all) return rc_all;
     return KFACB_OK;
 }
