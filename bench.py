@@ -14,9 +14,10 @@ ours (default): the CUDA path through the drop-in Python API / C ABI.
     barrier + synchronize on both sides, max over ranks).
   * `e2e`: the same step driven from pinned HOST buffers: per step H2D of every
     owned a / g and of all gradients, step(), D2H of all rewritten gradients.
-  * `roofline`: the dominant phase of the step (eigendecomposition) against the
-    tensor roofline, F = sum 9 n^3; all phases are listed
-    under `phases`.
+  * `roofline`: the dominant kernel of the step (the Jacobi row-update GEMM, HBM
+    bound) measured live with CUDA events in an extra untimed profiled step;
+    every phase is listed under `phases` with its algorithmic TFLOP/s and GB/s
+    (SURVEY.md section 8d conventions).
   * `cpu_baseline`: the oracle (CPU restatement of the reference) on this box's
     host cores on a bounded sample (one layer per distinct shape class, scaled by
     class multiplicity).
@@ -344,24 +345,40 @@ def run_ours(args):
     e2e_steps = max(1, min(args.steps, args.e2e_steps))
     e2e_ms = timed_loop(e2e_step, e2e_steps) / e2e_steps
 
-    # ---- roofline of the dominant phase ----
+    # ---- roofline of the dominant kernel ----
+    # One extra, UNTIMED step with KFACB_PROFILE=1: the library times its three per-round Jacobi kernels with
+    # CUDA events on the launching stream and reports their algorithmic HBM bytes (include/kfacb.h).
     peaks = load_peaks()
     owned_layers = [layers[i] for i in owned]
     work = algorithmic_work(owned_layers, batch, variant)
+    roofline = None
+    if variant == 'eigen_dp':
+        os.environ['KFACB_PROFILE'] = '1'
+        dev_step(0)
+        torch.cuda.synchronize()
+        os.environ.pop('KFACB_PROFILE', None)
+        prof = eng.eigh_last_profile()
+        if prof['ms_update'] > 0:
+            ach = prof['bytes_update'] / (prof['ms_update'] * 1e-3) / 1e9
+            roofline = dict(
+                bound='hbm', kernel='bj_update_tc_kernel (rows <- U^T rows, tcgen05 3xTF32; largest share of the step)',
+                achieved=ach, peak=peaks['hbm'], unit='GB/s', frac=ach / peaks['hbm'],
+                traffic=None,
+                launches=int(prof['rounds']), avg_launch_us=1e3 * prof['ms_update'] / max(1, prof['rounds']),
+                algorithmic_bytes_per_launch=prof['bytes_update'] / max(1, prof['rounds']),
+                share_of_step=prof['ms_update'] / ms_per_step,
+                other_kernels=dict(
+                    bj_h_tc_kernel=dict(ms=prof['ms_h'], gbs=prof['bytes_h'] / max(1e-9, prof['ms_h'] * 1e-3) / 1e9),
+                    bj_solve_kernel=dict(ms=prof['ms_solve'])),
+                peak_note='%s STREAM-copy HBM peak from MEASURED_PEAKS.json; algorithmic bytes = 16*n_pad^2 per active '
+                          'factor and round (W and V rows read once + written once); ncu DRAM traffic of the same kernel '
+                          'on one 4608-dim factor: profiles/r01_jacobi_kernels_ncu_full.csv (287 MB measured vs 340 MB '
+                          'algorithmic: L2 hits)' % peaks['src'])
     if world > 1:       # report the max-loaded rank's work alongside the max-over-ranks time
         wt = torch.tensor([float(work['F_inverse'])], device=dev)
         dist.all_reduce(wt, op=dist.ReduceOp.MAX)
         work['F_inverse'] = float(wt.item())
     tf32_peak = peaks['bf16_sustained'] / 2.0
-    inv_ms = phases.get('compute_inverse')
-    roofline = None
-    if inv_ms:
-        ach = work['F_inverse'] / (inv_ms * 1e-3) / 1e12
-        roofline = dict(bound='tensor', kernel='eigendecomposition phase (blocked Jacobi kernels)',
-                        achieved=ach, peak=tf32_peak, unit='TFLOP/s', frac=ach / tf32_peak,
-                        traffic=None,
-                        peak_note='dense TF32 = 1/2 of the %s sustained bf16 cuBLAS peak in '
-                                  'MEASURED_PEAKS.json; algorithmic flops = sum 9 n^3' % peaks['src'])
     phase_report = {}
     for name, key_f, key_b in (('compute_factors', 'F_factor', 'B_factor'),
                                ('compute_inverse', 'F_inverse', 'B_inverse'),
@@ -372,6 +389,7 @@ def run_ours(args):
             ent = dict(ms=ms)
             if key_f:
                 ent['tflops'] = work[key_f] / (ms * 1e-3) / 1e12
+                ent['frac_of_tf32_peak'] = ent['tflops'] / tf32_peak
             ent['gbs'] = work[key_b] / (ms * 1e-3) / 1e9
             phase_report[name] = ent
     if 'communicate_pred' in phases:

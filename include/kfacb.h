@@ -123,6 +123,14 @@ int    kfacb_eigh_batched(const int32_t* n, int32_t count,
                           void* workspace, size_t workspace_bytes,
                           kfacb_stream_t stream);
 
+/* Benchmark aid.  With the environment variable KFACB_PROFILE=1, kfacb_eigh_batched times its three
+ * per-round kernels with CUDA events (synchronising every round: never use it inside a timed region) and
+ * this call returns the totals of the last such run:
+ *   out8 = { rounds, ms projected-block kernel, ms solve kernel, ms update kernel,
+ *            algorithmic HBM bytes of the projected-block launches (8 n_pad^2 per active matrix and round),
+ *            algorithmic HBM bytes of the update launches (16 n_pad^2 ...), matrices, block pairs } */
+int    kfacb_eigh_last_profile(double* out8);
+
 /* ---------------------------------------------------------------------------
  * (2b) pi-damped SPD inverse.  Replaces
  * kfac/kfac_preconditioner_inv_dp.py:98-123, _add_value_to_diagonal

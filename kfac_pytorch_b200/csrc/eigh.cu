@@ -840,13 +840,27 @@ struct EpiToX {
 // ---------------------------------------------------------------------------
 // workspace plan
 // ---------------------------------------------------------------------------
-struct EighPlan {
-    int n_direct = 0, n_block = 0, total_pairs = 0, max_ksplit = 1, max_rounds = 0;
+// ---------------------------------------------------------------------------
+// workspace plan.  The blocked-path matrices are split into up to MAX_GROUPS groups (longest-processing-time
+// on n^3); every group runs its own round loop on its own internal stream, so the latency-bound solve kernel of
+// one group overlaps with the bandwidth-bound GEMM kernels of the others.
+// ---------------------------------------------------------------------------
+constexpr int MAX_GROUPS = 4;
+
+struct GroupPlan {
+    int nb = 0, total_pairs = 0, max_ksplit = 1, max_rounds = 0, nmax = 0;
     long max_ld = 0;
-    size_t off_dmats = 0, off_dindex = 0, off_bmats = 0, off_bindex = 0, off_pairmat = 0,
-           off_partoff = 0, off_state = 0, off_ubuf = 0, off_partial = 0, off_perm = 0,
-           off_lam = 0, off_x = 0, total = 0;
+    int idx[512];                 // indices (into the caller's arrays) of this group's matrices
+    size_t off_bmats = 0, off_bindex = 0, off_pairmat = 0, off_partoff = 0, off_state = 0, off_ubuf = 0,
+           off_partial = 0, off_perm = 0, off_lam = 0, off_x = 0;
 };
+struct EighPlan {
+    int n_direct = 0, n_block = 0, ngroups = 0;
+    size_t off_dmats = 0, off_dindex = 0, total = 0;
+    GroupPlan g[MAX_GROUPS];
+};
+
+static double g_profile[8] = {0};      // last KFACB_PROFILE=1 run: rounds, ms H/solve/update, bytes H/update, matrices, pairs
 
 static int env_int(const char* name, int dflt) {
     const char* v = getenv(name);
@@ -855,62 +869,130 @@ static int env_int(const char* name, int dflt) {
 
 static int bj_npad(int n) { return cdiv(n, BJ_B) * BJ_B; }
 
-static EighPlan make_plan(const int32_t* n, int count) {
-    EighPlan pl;
-    size_t x_bytes = 0, part_floats = 0, lam_floats = 0, perm_ints = 0;
+static bool make_plan(const int32_t* n, int count, EighPlan& pl) {
+    // block-path matrices, largest first (stable), dealt to the least-loaded group
+    int order[512 * MAX_GROUPS];
+    int nblock = 0;
     for (int i = 0; i < count; ++i) {
         if (n[i] <= 0) continue;
         if (n[i] <= DIRECT_MAX_N) { pl.n_direct++; continue; }
-        pl.n_block++;
-        const int np = bj_npad(n[i]);
-        const int nblk = np / BJ_B;
-        const int p = (nblk + 1) & ~1;
-        const int ks = cdiv(np, BJ_KCHUNK);
-        pl.total_pairs += p / 2;
-        if (ks > pl.max_ksplit) pl.max_ksplit = ks;
-        if ((p - 1) * 64 > pl.max_rounds) pl.max_rounds = (p - 1) * 64;   // hard cap; the device-side sweep limit ends earlier
-        if (2L * np > pl.max_ld) pl.max_ld = 2L * np;
-        x_bytes += align_up((size_t)np * 2 * np * sizeof(float), 256);
-        part_floats += (size_t)(p / 2) * ks * BJ_M * BJ_M;
-        lam_floats += 2 * (size_t)np;
-        perm_ints += (size_t)np;
+        if (nblock >= 512 * MAX_GROUPS) return false;
+        order[nblock++] = i;
+    }
+    pl.n_block = nblock;
+    for (int a = 1; a < nblock; ++a) {           // insertion sort by n descending (stable)
+        const int v = order[a];
+        int b = a - 1;
+        while (b >= 0 && n[order[b]] < n[v]) { order[b + 1] = order[b]; --b; }
+        order[b + 1] = v;
+    }
+    int want = env_int("KFACB_EIGH_GROUPS", 3);
+    if (env_int("KFACB_PROFILE", 0)) want = 1;   // the per-round profiler serialises one group
+    if (want < 1) want = 1;
+    if (want > MAX_GROUPS) want = MAX_GROUPS;
+    pl.ngroups = nblock < want ? nblock : want;
+    double load[MAX_GROUPS] = {0};
+    for (int a = 0; a < nblock; ++a) {
+        int best = 0;
+        for (int k = 1; k < pl.ngroups; ++k) if (load[k] < load[best]) best = k;
+        GroupPlan& g = pl.g[best];
+        if (g.nb >= 512) return false;
+        g.idx[g.nb++] = order[a];
+        load[best] += (double)n[order[a]] * n[order[a]] * n[order[a]];
     }
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off += align_up(bytes, 256); return o; };
     pl.off_dmats = take(sizeof(DirectMat) * (size_t)(pl.n_direct + 1));
     pl.off_dindex = take(sizeof(int) * (size_t)(pl.n_direct + 1));
-    pl.off_bmats = take(sizeof(BjMat) * (size_t)(pl.n_block + 1));
-    pl.off_bindex = take(sizeof(int) * (size_t)(pl.n_block + 1));
-    pl.off_pairmat = take(sizeof(int) * (size_t)(pl.total_pairs + 1));
-    pl.off_partoff = take(sizeof(long) * (size_t)(pl.n_block + 1));
-    pl.off_state = take(sizeof(BjState) * (size_t)(pl.n_block + 1));
-    pl.off_ubuf = take(sizeof(float) * (size_t)pl.total_pairs * BJ_M * BJ_M);
-    pl.off_partial = take(sizeof(float) * part_floats);
-    pl.off_perm = take(sizeof(int) * perm_ints);
-    pl.off_lam = take(sizeof(float) * lam_floats);
-    pl.off_x = take(x_bytes);
+    for (int k = 0; k < pl.ngroups; ++k) {
+        GroupPlan& g = pl.g[k];
+        size_t x_bytes = 0, part_floats = 0, lam_floats = 0, perm_ints = 0;
+        for (int a = 0; a < g.nb; ++a) {
+            const int nn = n[g.idx[a]];
+            const int np = bj_npad(nn);
+            const int nblk = np / BJ_B;
+            const int p = (nblk + 1) & ~1;
+            const int ks = cdiv(np, BJ_KCHUNK);
+            g.total_pairs += p / 2;
+            if (ks > g.max_ksplit) g.max_ksplit = ks;
+            if ((p - 1) * 64 > g.max_rounds) g.max_rounds = (p - 1) * 64;   // hard cap; the device-side sweep limit ends earlier
+            if (2L * np > g.max_ld) g.max_ld = 2L * np;
+            if (nn > g.nmax) g.nmax = nn;
+            x_bytes += align_up((size_t)np * 2 * np * sizeof(float), 256);
+            part_floats += (size_t)(p / 2) * ks * BJ_M * BJ_M;
+            lam_floats += 2 * (size_t)np;
+            perm_ints += (size_t)np;
+        }
+        g.off_bmats = take(sizeof(BjMat) * (size_t)(g.nb + 1));
+        g.off_bindex = take(sizeof(int) * (size_t)(g.nb + 1));
+        g.off_pairmat = take(sizeof(int) * (size_t)(g.total_pairs + 1));
+        g.off_partoff = take(sizeof(long) * (size_t)(g.nb + 1));
+        g.off_state = take(sizeof(BjState) * (size_t)(g.nb + 1));
+        g.off_ubuf = take(sizeof(float) * (size_t)g.total_pairs * BJ_M * BJ_M);
+        g.off_partial = take(sizeof(float) * part_floats);
+        g.off_perm = take(sizeof(int) * perm_ints);
+        g.off_lam = take(sizeof(float) * lam_floats);
+        g.off_x = take(x_bytes);
+    }
     pl.total = off + 256;
-    return pl;
+    return true;
 }
 
-static int* host_active_flag(int** dev_ptr) {
-    static int* h = nullptr;
-    static int* d = nullptr;
-    if (!h) {
-        if (cudaHostAlloc((void**)&h, sizeof(int), cudaHostAllocMapped) != cudaSuccess) return nullptr;
-        if (cudaHostGetDevicePointer((void**)&d, h, 0) != cudaSuccess) return nullptr;
-        *h = 1;
+// pinned, device-mapped progress flags (one per group) + the internal streams / events of the groups
+struct GroupRuntime {
+    int* h_active = nullptr;      // [MAX_GROUPS] host view
+    int* d_active = nullptr;      // device view
+    cudaStream_t stream[MAX_GROUPS] = {nullptr};
+    cudaEvent_t fork = nullptr, join[MAX_GROUPS] = {nullptr}, prog[MAX_GROUPS][2] = {{nullptr}};
+    bool ok = false;
+};
+static GroupRuntime* group_runtime() {
+    static GroupRuntime rt;
+    if (!rt.ok) {
+        if (cudaHostAlloc((void**)&rt.h_active, sizeof(int) * MAX_GROUPS, cudaHostAllocMapped) != cudaSuccess) return nullptr;
+        if (cudaHostGetDevicePointer((void**)&rt.d_active, rt.h_active, 0) != cudaSuccess) return nullptr;
+        if (cudaEventCreateWithFlags(&rt.fork, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+        for (int k = 0; k < MAX_GROUPS; ++k) {
+            if (cudaStreamCreateWithFlags(&rt.stream[k], cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+            if (cudaEventCreateWithFlags(&rt.join[k], cudaEventDisableTiming) != cudaSuccess) return nullptr;
+            for (int e = 0; e < 2; ++e)
+                if (cudaEventCreateWithFlags(&rt.prog[k][e], cudaEventDisableTiming) != cudaSuccess) return nullptr;
+        }
+        rt.ok = true;
     }
-    *dev_ptr = d;
-    return h;
+    return &rt;
 }
+
+// host-side state of one group while its rounds are being enqueued
+struct GroupRun {
+    const GroupPlan* gp = nullptr;
+    BjMat* hm = nullptr;
+    const BjMat* dm = nullptr;
+    const int* dpm = nullptr;
+    const long* dpoff = nullptr;
+    BjState* dstate = nullptr;
+    float* ubuf = nullptr;
+    float* partial = nullptr;
+    cudaStream_t st = nullptr;
+    bool done = false;
+};
 
 }  // namespace kfacb
 
 using namespace kfacb;
 
+extern "C" int kfacb_eigh_last_profile(double* out8) {
+    if (!out8) return KFACB_ERR_ARG;
+    for (int i = 0; i < 8; ++i) out8[i] = g_profile[i];
+    return KFACB_OK;
+}
+
 extern "C" size_t kfacb_eigh_workspace_bytes(const int32_t* n, int32_t count) {
-    return make_plan(n, count).total;
+    EighPlan* pl = new EighPlan();
+    const bool ok = make_plan(n, count, *pl);
+    const size_t t = ok ? pl->total : 0;
+    delete pl;
+    return t;
 }
 
 extern "C" int kfacb_eigh_batched(const int32_t* n, int32_t count,
@@ -920,12 +1002,27 @@ extern "C" int kfacb_eigh_batched(const int32_t* n, int32_t count,
                                   kfacb_stream_t stream) {
     cudaStream_t st = (cudaStream_t)stream;
     KFACB_REQUIRE(n && M && Q && d && count >= 0, "null argument");
-    const EighPlan pl = make_plan(n, count);
+    EighPlan* plp = new EighPlan();
+    struct PlanGuard { EighPlan* p; ~PlanGuard() { delete p; } } plan_guard{plp};
+    KFACB_REQUIRE(make_plan(n, count, *plp), "too many matrices in one eigh batch");
+    const EighPlan& pl = *plp;
     if (workspace_bytes < pl.total || ((uintptr_t)workspace & 255)) {
         set_error("eigh workspace too small or misaligned (%zu < %zu)", workspace_bytes, pl.total);
         return KFACB_ERR_WORKSPACE;
     }
     char* ws = (char*)workspace;
+    for (int i = 0; i < count; ++i)
+        KFACB_REQUIRE(n[i] <= 8192, "matrix %d: n = %d > 8192 is not supported by the in-kernel eigenvalue sort", i, n[i]);
+    GroupRuntime* rt = nullptr;
+    const bool single = (pl.ngroups <= 1);       // one group runs directly on the caller's stream
+    if (pl.n_block > 0) {
+        rt = group_runtime();
+        if (!rt) { set_error("cannot create the eigh streams / events / progress flags"); return KFACB_ERR_CUDA; }
+        if (!single) {                           // fork now: the groups need not wait for the small-matrix kernel below
+            KFACB_CHECK_CUDA(cudaEventRecord(rt->fork, st));
+            for (int k = 0; k < pl.ngroups; ++k) KFACB_CHECK_CUDA(cudaStreamWaitEvent(rt->stream[k], rt->fork, 0));
+        }
+    }
 
     // ---- direct path ----
     if (pl.n_direct > 0) {
@@ -955,19 +1052,35 @@ extern "C" int kfacb_eigh_batched(const int32_t* n, int32_t count,
     if (pl.n_block == 0) return KFACB_OK;
 
     // ---- blocked path ----
-    BjMat* hm = new BjMat[pl.n_block];
-    int* hidx = new int[pl.n_block];
-    long* hpoff = new long[pl.n_block];
-    int* hpm = new int[pl.total_pairs];
-    struct Guard { BjMat* a; int* b; long* c; int* d; ~Guard() { delete[] a; delete[] b; delete[] c; delete[] d; } } guard{hm, hidx, hpoff, hpm};
-    {
-        size_t xo = pl.off_x, lo = pl.off_lam, po = pl.off_perm;
+    for (int i = 0; i < count; ++i)
+        if (n[i] > DIRECT_MAX_N) KFACB_REQUIRE(M[i] && Q[i] && d[i], "matrix %d: null pointer", i);
+    const bool prof = env_int("KFACB_PROFILE", 0) != 0;
+    const int inner_sweeps = env_int("KFACB_INNER_SWEEPS", BJ_INNER_SWEEPS);   // tuning knobs
+    const int full_inner = env_int("KFACB_FULL_INNER", 0);                     // 1 = full inner tournament every visit
+    const int max_sweeps = env_int("KFACB_MAX_SWEEPS", BJ_MAX_SWEEPS);
+    const int upd_g = max(1, env_int("KFACB_UPD_TILES", 8));                   // 128-column tiles per update CTA
+    KFACB_CHECK_CUDA(cudaFuncSetAttribute(bj_h_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tcg::SMEM));
+    KFACB_CHECK_CUDA(cudaFuncSetAttribute(bj_update_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, UPD_SMEM));
+    KFACB_CHECK_CUDA(cudaFuncSetAttribute(bj_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SOLVE_SMEM));
+
+    const int G = pl.ngroups;
+    GroupRun run[MAX_GROUPS];
+    struct RunGuard { GroupRun* r; int g; ~RunGuard() { for (int k = 0; k < g; ++k) delete[] r[k].hm; } } run_guard{run, G};
+    for (int k = 0; k < G; ++k) {
+        const GroupPlan& gp = pl.g[k];
+        GroupRun& gr = run[k];
+        gr.gp = &gp;
+        gr.st = single ? st : rt->stream[k];
+        gr.hm = new BjMat[gp.nb];
+        int* hidx = new int[gp.nb];
+        long* hpoff = new long[gp.nb];
+        int* hpm = new int[gp.total_pairs];
+        size_t xo = gp.off_x, lo = gp.off_lam, po = gp.off_perm;
         long partial_off = 0;
-        int k = 0, pair = 0;
-        for (int i = 0; i < count; ++i) {
-            if (n[i] <= DIRECT_MAX_N) continue;
-            KFACB_REQUIRE(M[i] && Q[i] && d[i], "matrix %d: null pointer", i);
-            BjMat& b = hm[k];
+        int pair = 0;
+        for (int a = 0; a < gp.nb; ++a) {
+            const int i = gp.idx[a];
+            BjMat& b = gr.hm[a];
             b.n = n[i]; b.n_pad = bj_npad(n[i]); b.nblk = b.n_pad / BJ_B; b.p = (b.nblk + 1) & ~1;
             b.A = M[i]; b.Q = Q[i]; b.d = d[i];
             b.X = (float*)(ws + xo); xo += align_up((size_t)b.n_pad * 2 * b.n_pad * sizeof(float), 256);
@@ -976,122 +1089,140 @@ extern "C" int kfacb_eigh_batched(const int32_t* n, int32_t count,
             b.pair_begin = pair; b.ksplit = cdiv(b.n_pad, BJ_KCHUNK);
             // few blocks = short sweeps and little quadratic tail: ask for more before stopping (these are cheap)
             b.tol_conv = 1e-6f * (float)env_int("KFACB_CONV_TOL_E6", b.p >= 16 ? 100 : 20);
-            hpoff[k] = partial_off;
+            hpoff[a] = partial_off;
             partial_off += (long)(b.p / 2) * b.ksplit * BJ_M * BJ_M;
-            for (int q = 0; q < b.p / 2; ++q) hpm[pair++] = k;
-            hidx[k] = i;
-            ++k;
+            for (int q = 0; q < b.p / 2; ++q) hpm[pair++] = a;
+            hidx[a] = i;
         }
-    }
-    const int nb = pl.n_block;
-    KFACB_CHECK_CUDA(cudaMemcpyAsync(ws + pl.off_bmats, hm, sizeof(BjMat) * nb, cudaMemcpyHostToDevice, st));
-    KFACB_CHECK_CUDA(cudaMemcpyAsync(ws + pl.off_bindex, hidx, sizeof(int) * nb, cudaMemcpyHostToDevice, st));
-    KFACB_CHECK_CUDA(cudaMemcpyAsync(ws + pl.off_partoff, hpoff, sizeof(long) * nb, cudaMemcpyHostToDevice, st));
-    KFACB_CHECK_CUDA(cudaMemcpyAsync(ws + pl.off_pairmat, hpm, sizeof(int) * pl.total_pairs, cudaMemcpyHostToDevice, st));
-    KFACB_CHECK_CUDA(cudaMemsetAsync(ws + pl.off_state, 0, sizeof(BjState) * nb, st));
-    const BjMat* dm = (const BjMat*)(ws + pl.off_bmats);
-    const int* dpm = (const int*)(ws + pl.off_pairmat);
-    const long* dpoff = (const long*)(ws + pl.off_partoff);
-    BjState* dstate = (BjState*)(ws + pl.off_state);
-    float* ubuf = (float*)(ws + pl.off_ubuf);
-    float* partial = (float*)(ws + pl.off_partial);
-
-    int* d_active = nullptr;
-    int* h_active = host_active_flag(&d_active);
-    if (!h_active) { set_error("cannot allocate the pinned progress flag"); return KFACB_ERR_CUDA; }
-    *h_active = 1;
-
-    bj_init_kernel<<<dim3(4 * sm_count(), nb), 256, 0, st>>>(dm, dstate);
-    KFACB_CHECK_LAUNCH();
-
-    const int col_tiles = cdiv(pl.max_ld, TILE);
-    constexpr int CH = 24;            // rounds per progress chunk (host look-ahead = 2 chunks)
-    cudaEvent_t ev[2];
-    KFACB_CHECK_CUDA(cudaEventCreateWithFlags(&ev[0], cudaEventDisableTiming));
-    KFACB_CHECK_CUDA(cudaEventCreateWithFlags(&ev[1], cudaEventDisableTiming));
-    int rc = KFACB_OK;
-    const bool prof = env_int("KFACB_PROFILE", 0) != 0;
-    cudaEvent_t pev[4];
-    double ptime[3] = {0, 0, 0};
-    int prounds = 0;
-    if (prof) for (int k = 0; k < 4; ++k) cudaEventCreate(&pev[k]);
-    const int inner_sweeps = env_int("KFACB_INNER_SWEEPS", BJ_INNER_SWEEPS);   // tuning knobs
-    const int full_inner = env_int("KFACB_FULL_INNER", 0);                     // 1 = full inner tournament every visit
-    const int max_sweeps = env_int("KFACB_MAX_SWEEPS", BJ_MAX_SWEEPS);
-    KFACB_CHECK_CUDA(cudaFuncSetAttribute(bj_h_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tcg::SMEM));
-    KFACB_CHECK_CUDA(cudaFuncSetAttribute(bj_update_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, UPD_SMEM));
-    const int upd_g = max(1, env_int("KFACB_UPD_TILES", 8));                   // 128-column tiles per update CTA
-    KFACB_CHECK_CUDA(cudaFuncSetAttribute(bj_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SOLVE_SMEM));
-    for (int r = 0; r < pl.max_rounds; ++r) {
-        if (r % CH == 0 && r >= 2 * CH) {
-            if (cudaEventSynchronize(ev[(r / CH) & 1]) != cudaSuccess) { rc = KFACB_ERR_CUDA; set_error("event sync failed"); break; }
-            if (*(volatile int*)h_active == 0) break;
-        }
-        if (prof) cudaEventRecord(pev[0], st);
-        bj_h_tc_kernel<<<dim3(pl.max_ksplit, pl.total_pairs), tcg::THREADS, tcg::SMEM, st>>>(dm, dpm, dstate, r, partial, dpoff);
-        if (prof) cudaEventRecord(pev[1], st);
-        bj_solve_kernel<<<pl.total_pairs, SOLVE_THREADS, SOLVE_SMEM, st>>>(dm, dpm, dstate, r, partial, dpoff, ubuf, inner_sweeps, full_inner);
-        if (prof) cudaEventRecord(pev[2], st);
-        bj_update_tc_kernel<<<dim3(cdiv(col_tiles, upd_g), pl.total_pairs), UPD_THREADS, UPD_SMEM, st>>>(dm, dpm, dstate, r, ubuf, upd_g);
-        if (prof) {          // KFACB_PROFILE=1: per-kernel time of every round (debug only: synchronises each round)
-            cudaEventRecord(pev[3], st);
-            cudaEventSynchronize(pev[3]);
-            float t;
-            for (int k = 0; k < 3; ++k) { cudaEventElapsedTime(&t, pev[k], pev[k + 1]); ptime[k] += t; }
-            ++prounds;
-        }
-        bool boundary = false;
-        for (int k = 0; k < nb && !boundary; ++k) boundary = ((r + 1) % (hm[k].p - 1)) == 0;
-        if (boundary) { bj_check_kernel<<<1, 256, 0, st>>>(dm, dstate, nb, r, max_sweeps, d_active); count_launch(1); }
-        count_launch(3);
-        if (cudaGetLastError() != cudaSuccess) { rc = KFACB_ERR_CUDA; set_error("jacobi round launch failed"); break; }
-        if (r % CH == CH - 1) cudaEventRecord(ev[(r / CH) & 1], st);
-    }
-    cudaEventDestroy(ev[0]); cudaEventDestroy(ev[1]);
-    if (prof) {
-        fprintf(stderr, "[kfacb eigh profile] matrices=%d pairs=%d rounds=%d  H %.1f ms  solve %.1f ms  update %.1f ms\n",
-                nb, pl.total_pairs, prounds, ptime[0], ptime[1], ptime[2]);
-        for (int k = 0; k < 4; ++k) cudaEventDestroy(pev[k]);
-    }
-    if (rc) return rc;
-
-    // one Newton-Schulz step removes the orthogonality drift of ~1e3 accumulated fp32 rotations
-    if (env_int("KFACB_NS", 1)) {
-        for (int k = 0; k < nb; ++k) {
-            const BjMat& b = hm[k];
-            const long ld = 2L * b.n_pad;
-            LdKContig lv{b.X + b.n_pad, ld, b.n, b.n};
-            KFACB_CHECK_CUDA(launch_gemm(lv, lv, EpiGramMinusI{b.X, ld}, b.n, b.n, b.n, st));   // V V^T - I cancels to ~1e-6: exact fp32 FMAs, not 3xTF32
-            LdKContig le{b.X, ld, b.n, b.n};
-            LdMnContig lvt{b.X + b.n_pad, ld, b.n, b.n};
-            KFACB_CHECK_CUDA(launch_gemm(le, lvt, EpiNsUpdate{b.Q, b.X, ld, b.n, b.n_pad}, b.n, b.n, b.n, st));
-            KFACB_CHECK_CUDA(cudaMemcpy2DAsync(b.X + b.n_pad, ld * sizeof(float), b.Q, (size_t)b.n * sizeof(float),
-                                               (size_t)b.n * sizeof(float), b.n, cudaMemcpyDeviceToDevice, st));
-        }
-    }
-    // Rayleigh quotients: Y = V^T A  (row i of Y = A v_i), written over the W half
-    for (int k = 0; k < nb; ++k) {
-        const BjMat& b = hm[k];
-        LdKContig la{b.X + b.n_pad, 2L * b.n_pad, b.n, b.n};
-        LdMnContig lb{b.A, (long)b.n, b.n, b.n};
-        EpiToX epi{b.X, 2L * b.n_pad};
-        KFACB_CHECK_CUDA(launch_gemm(la, lb, epi, b.n, b.n, b.n, st));
-    }
-    int nmax = 0;
-    for (int k = 0; k < nb; ++k) if (hm[k].n > nmax) nmax = hm[k].n;
-    bj_rayleigh_kernel<<<dim3(cdiv(nmax, 8), nb), 256, 0, st>>>(dm);
-    KFACB_CHECK_LAUNCH();
-    int np2 = 1;
-    while (np2 < nmax) np2 <<= 1;
-    const size_t sort_smem = (size_t)np2 * 8;
-    KFACB_CHECK_CUDA(cudaFuncSetAttribute(bj_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sort_smem));
-    bj_sort_kernel<<<nb, 1024, sort_smem, st>>>(dm, eps_floor);
-    KFACB_CHECK_LAUNCH();
-    bj_write_kernel<<<dim3(cdiv(nmax, 32), cdiv(nmax, 32), nb), 256, 0, st>>>(dm);
-    KFACB_CHECK_LAUNCH();
-    if (sweeps_out) {
-        bj_store_sweeps_kernel<<<cdiv(nb, 128), 128, 0, st>>>(dstate, (const int*)(ws + pl.off_bindex), nb, sweeps_out);
+        cudaError_t e1 = cudaMemcpyAsync(ws + gp.off_bmats, gr.hm, sizeof(BjMat) * gp.nb, cudaMemcpyHostToDevice, gr.st);
+        cudaError_t e2 = cudaMemcpyAsync(ws + gp.off_bindex, hidx, sizeof(int) * gp.nb, cudaMemcpyHostToDevice, gr.st);
+        cudaError_t e3 = cudaMemcpyAsync(ws + gp.off_partoff, hpoff, sizeof(long) * gp.nb, cudaMemcpyHostToDevice, gr.st);
+        cudaError_t e4 = cudaMemcpyAsync(ws + gp.off_pairmat, hpm, sizeof(int) * gp.total_pairs, cudaMemcpyHostToDevice, gr.st);
+        cudaError_t e5 = cudaMemsetAsync(ws + gp.off_state, 0, sizeof(BjState) * gp.nb, gr.st);
+        delete[] hidx; delete[] hpoff; delete[] hpm;
+        KFACB_CHECK_CUDA(e1); KFACB_CHECK_CUDA(e2); KFACB_CHECK_CUDA(e3); KFACB_CHECK_CUDA(e4); KFACB_CHECK_CUDA(e5);
+        gr.dm = (const BjMat*)(ws + gp.off_bmats);
+        gr.dpm = (const int*)(ws + gp.off_pairmat);
+        gr.dpoff = (const long*)(ws + gp.off_partoff);
+        gr.dstate = (BjState*)(ws + gp.off_state);
+        gr.ubuf = (float*)(ws + gp.off_ubuf);
+        gr.partial = (float*)(ws + gp.off_partial);
+        rt->h_active[k] = 1;
+        bj_init_kernel<<<dim3(4 * sm_count(), gp.nb), 256, 0, gr.st>>>(gr.dm, gr.dstate);
         KFACB_CHECK_LAUNCH();
     }
-    return KFACB_OK;
+
+    // ---- round loop: the groups' rounds are enqueued interleaved, each on its own stream ----
+    constexpr int CH = 24;            // rounds per progress chunk (host look-ahead = 2 chunks)
+    int rc = KFACB_OK;
+    cudaEvent_t pev[4];
+    double ptime[3] = {0, 0, 0}, pbytes[2] = {0, 0};
+    int prounds = 0;
+    BjState* hstate = prof ? new BjState[pl.g[0].nb] : nullptr;
+    if (prof) for (int k = 0; k < 4; ++k) cudaEventCreate(&pev[k]);
+    int max_rounds = 0;
+    for (int k = 0; k < G; ++k) if (pl.g[k].max_rounds > max_rounds) max_rounds = pl.g[k].max_rounds;
+    for (int r = 0; r < max_rounds && rc == KFACB_OK; ++r) {
+        bool any_active = false;
+        for (int k = 0; k < G; ++k) {
+            GroupRun& gr = run[k];
+            const GroupPlan& gp = *gr.gp;
+            if (gr.done || r >= gp.max_rounds) continue;
+            if (r % CH == 0 && r >= 2 * CH) {
+                if (cudaEventSynchronize(rt->prog[k][(r / CH) & 1]) != cudaSuccess) { rc = KFACB_ERR_CUDA; set_error("event sync failed"); break; }
+                if (((volatile int*)rt->h_active)[k] == 0) { gr.done = true; continue; }
+            }
+            any_active = true;
+            const int col_tiles = cdiv(gp.max_ld, TILE);
+            if (prof) cudaEventRecord(pev[0], gr.st);
+            bj_h_tc_kernel<<<dim3(gp.max_ksplit, gp.total_pairs), tcg::THREADS, tcg::SMEM, gr.st>>>(gr.dm, gr.dpm, gr.dstate, r, gr.partial, gr.dpoff);
+            if (prof) cudaEventRecord(pev[1], gr.st);
+            bj_solve_kernel<<<gp.total_pairs, SOLVE_THREADS, SOLVE_SMEM, gr.st>>>(gr.dm, gr.dpm, gr.dstate, r, gr.partial, gr.dpoff, gr.ubuf, inner_sweeps, full_inner);
+            if (prof) cudaEventRecord(pev[2], gr.st);
+            bj_update_tc_kernel<<<dim3(cdiv(col_tiles, upd_g), gp.total_pairs), UPD_THREADS, UPD_SMEM, gr.st>>>(gr.dm, gr.dpm, gr.dstate, r, gr.ubuf, upd_g);
+            if (prof) {          // KFACB_PROFILE=1: per-kernel time of every round (debug only: synchronises each round)
+                cudaEventRecord(pev[3], gr.st);
+                cudaEventSynchronize(pev[3]);
+                float t;
+                for (int e = 0; e < 3; ++e) { cudaEventElapsedTime(&t, pev[e], pev[e + 1]); ptime[e] += t; }
+                ++prounds;
+                // algorithmic HBM bytes of this round: every ACTIVE matrix has its W and V rows read once by the
+                // projected-block kernel (8 n_pad^2) and read + written once by the update kernel (16 n_pad^2)
+                if (cudaMemcpy(hstate, gr.dstate, sizeof(BjState) * gp.nb, cudaMemcpyDeviceToHost) == cudaSuccess)
+                    for (int a = 0; a < gp.nb; ++a)
+                        if (!hstate[a].converged) {
+                            const double n2 = (double)gr.hm[a].n_pad * gr.hm[a].n_pad;
+                            pbytes[0] += 8.0 * n2; pbytes[1] += 16.0 * n2;
+                        }
+            }
+            bool boundary = false;
+            for (int a = 0; a < gp.nb && !boundary; ++a) boundary = ((r + 1) % (gr.hm[a].p - 1)) == 0;
+            if (boundary) {
+                bj_check_kernel<<<1, 256, 0, gr.st>>>(gr.dm, gr.dstate, gp.nb, r, max_sweeps, rt->d_active + k);
+                count_launch(1);
+            }
+            count_launch(3);
+            if (cudaGetLastError() != cudaSuccess) { rc = KFACB_ERR_CUDA; set_error("jacobi round launch failed"); break; }
+            if (r % CH == CH - 1) cudaEventRecord(rt->prog[k][(r / CH) & 1], gr.st);
+        }
+        if (!any_active) break;
+    }
+    if (prof) {
+        fprintf(stderr, "[kfacb eigh profile] matrices=%d pairs=%d rounds=%d  H %.1f ms  solve %.1f ms  update %.1f ms\n",
+                pl.g[0].nb, pl.g[0].total_pairs, prounds, ptime[0], ptime[1], ptime[2]);
+        for (int k = 0; k < 4; ++k) cudaEventDestroy(pev[k]);
+        g_profile[0] = prounds; g_profile[1] = ptime[0]; g_profile[2] = ptime[1]; g_profile[3] = ptime[2];
+        g_profile[4] = pbytes[0]; g_profile[5] = pbytes[1]; g_profile[6] = pl.g[0].nb; g_profile[7] = pl.g[0].total_pairs;
+        delete[] hstate;
+    }
+
+    // ---- per group: re-orthogonalise, Rayleigh quotients, sort, write; then join the caller's stream ----
+    for (int k = 0; k < G && rc == KFACB_OK; ++k) {
+        GroupRun& gr = run[k];
+        const GroupPlan& gp = *gr.gp;
+        cudaStream_t gs = gr.st;
+        // one Newton-Schulz step removes the orthogonality drift of ~1e3 accumulated fp32 rotations
+        if (env_int("KFACB_NS", 1)) {
+            for (int a = 0; a < gp.nb; ++a) {
+                const BjMat& b = gr.hm[a];
+                const long ld = 2L * b.n_pad;
+                LdKContig lv{b.X + b.n_pad, ld, b.n, b.n};
+                KFACB_CHECK_CUDA(launch_gemm(lv, lv, EpiGramMinusI{b.X, ld}, b.n, b.n, b.n, gs));   // V V^T - I cancels to ~1e-6: exact fp32 FMAs, not 3xTF32
+                LdKContig le{b.X, ld, b.n, b.n};
+                LdMnContig lvt{b.X + b.n_pad, ld, b.n, b.n};
+                KFACB_CHECK_CUDA(launch_gemm_auto(le, lvt, EpiNsUpdate{b.Q, b.X, ld, b.n, b.n_pad}, b.n, b.n, b.n, gs));   // E ~ 1e-5: 3xTF32 is ample
+                KFACB_CHECK_CUDA(cudaMemcpy2DAsync(b.X + b.n_pad, ld * sizeof(float), b.Q, (size_t)b.n * sizeof(float),
+                                                   (size_t)b.n * sizeof(float), b.n, cudaMemcpyDeviceToDevice, gs));
+            }
+        }
+        // Rayleigh quotients: Y = V^T A  (row i of Y = A v_i), written over the W half
+        for (int a = 0; a < gp.nb; ++a) {
+            const BjMat& b = gr.hm[a];
+            LdKContig la{b.X + b.n_pad, 2L * b.n_pad, b.n, b.n};
+            LdMnContig lb{b.A, (long)b.n, b.n, b.n};
+            EpiToX epi{b.X, 2L * b.n_pad};
+            KFACB_CHECK_CUDA(launch_gemm_auto(la, lb, epi, b.n, b.n, b.n, gs));
+        }
+        bj_rayleigh_kernel<<<dim3(cdiv(gp.nmax, 8), gp.nb), 256, 0, gs>>>(gr.dm);
+        KFACB_CHECK_LAUNCH();
+        int np2 = 1;
+        while (np2 < gp.nmax) np2 <<= 1;
+        const size_t sort_smem = (size_t)np2 * 8;
+        KFACB_CHECK_CUDA(cudaFuncSetAttribute(bj_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 8192));
+        bj_sort_kernel<<<gp.nb, 1024, sort_smem, gs>>>(gr.dm, eps_floor);
+        KFACB_CHECK_LAUNCH();
+        bj_write_kernel<<<dim3(cdiv(gp.nmax, 32), cdiv(gp.nmax, 32), gp.nb), 256, 0, gs>>>(gr.dm);
+        KFACB_CHECK_LAUNCH();
+        if (sweeps_out) {
+            bj_store_sweeps_kernel<<<cdiv(gp.nb, 128), 128, 0, gs>>>(gr.dstate, (const int*)(ws + gp.off_bindex), gp.nb, sweeps_out);
+            KFACB_CHECK_LAUNCH();
+        }
+    }
+    if (!single) {                               // always join, also on the error path
+        for (int k = 0; k < G; ++k) {
+            cudaEventRecord(rt->join[k], rt->stream[k]);
+            cudaStreamWaitEvent(st, rt->join[k], 0);
+        }
+    }
+    return rc;
 }

@@ -37,7 +37,7 @@ class LayerDesc(C.Structure):
 EXPORTS = [
     'kfacb_version', 'kfacb_launch_count', 'kfacb_last_error', 'kfacb_device_info', 'kfacb_layer_dA', 'kfacb_layer_dG',
     'kfacb_factor_workspace_bytes', 'kfacb_factor_update',
-    'kfacb_eigh_workspace_bytes', 'kfacb_eigh_batched',
+    'kfacb_eigh_workspace_bytes', 'kfacb_eigh_batched', 'kfacb_eigh_last_profile',
     'kfacb_spd_inverse_workspace_bytes', 'kfacb_pi_damped_inverse',
     'kfacb_precond_workspace_bytes', 'kfacb_precond_eigen', 'kfacb_precond_inverse',
     'kfacb_finalize_workspace_bytes', 'kfacb_finalize_grads',
@@ -80,6 +80,7 @@ def load_library(path: Optional[str] = None):
     lib.kfacb_eigh_workspace_bytes.restype = C.c_size_t
     lib.kfacb_eigh_batched.argtypes = [I32P, C.c_int32, PP, PP, PP, C.c_float, C.c_void_p,
                                        C.c_void_p, C.c_size_t, C.c_void_p]
+    lib.kfacb_eigh_last_profile.argtypes = [C.POINTER(C.c_double)]
     lib.kfacb_spd_inverse_workspace_bytes.argtypes = [I32P, I32P, C.c_int32]
     lib.kfacb_spd_inverse_workspace_bytes.restype = C.c_size_t
     lib.kfacb_pi_damped_inverse.argtypes = [I32P, I32P, C.c_int32, PP, PP, PP, PP, C.c_float,
@@ -189,6 +190,13 @@ class NativeEngine:
                 ns, n, _ptrs(mats), _ptrs(Qs), _ptrs(ds), eps_floor,
                 None if sweeps_out is None else sweeps_out.data_ptr(),
                 ws.data_ptr(), ws.numel(), self._stream()))
+
+    def eigh_last_profile(self):
+        """Totals of the last KFACB_PROFILE=1 eigh call (see include/kfacb.h)."""
+        out = (C.c_double * 8)()
+        self._call(self.lib.kfacb_eigh_last_profile(out))
+        keys = ('rounds', 'ms_h', 'ms_solve', 'ms_update', 'bytes_h', 'bytes_update', 'matrices', 'pairs')
+        return dict(zip(keys, list(out)))
 
     # -- (2b) pi-damped inverse ---------------------------------------------
     def pi_damped_inverse(self, A, G, invA, invG, damping: float):
