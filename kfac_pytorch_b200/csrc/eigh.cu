@@ -327,8 +327,8 @@ bj_h_tc_kernel(const BjMat* mats, const int* pair_mat, const BjState* state, int
     const int kbeg = zchunk * BJ_KCHUNK, kend = min(mt.n_pad, kbeg + BJ_KCHUNK);
     LdPairRows lv{mt.X + mt.n_pad, ld, bi * BJ_B, bj * BJ_B, kend};      // V rows
     LdPairRows lw{mt.X, ld, bi * BJ_B, bj * BJ_B, kend};                 // W rows
-    tcg::mainloop(lv, lw, 0, 0, kbeg, kend, false, c);
-    const float* d = tcg::drain(c, true);
+    tcg::mainloop<false>(lv, lw, 0, 0, kbeg, kend, false, c);     // 64 K-steps per chunk; H only steers the rotations
+    const float* d = tcg::drain<false>(c, true);
     float* dst = partial + partial_off[mi] +
                  ((long)(pair_idx - mt.pair_begin) * mt.ksplit + zchunk) * (BJ_M * BJ_M);
     for (int e = threadIdx.x; e < BJ_M * BJ_M; e += tcg::THREADS)

@@ -177,8 +177,8 @@ tc_syrk_ema_kernel(L ld, int n, int K, int kchunk, float scale, float alpha, int
     tri_decode(blockIdx.x, T, ti, tj);
     const int kbeg = blockIdx.y * kchunk;
     const int kend = min(K, kbeg + kchunk);
-    tcg::mainloop(ld, ld, ti * TILE, tj * TILE, kbeg, kend, ti == tj, c);
-    const float* d = tcg::drain(c, kend > kbeg);
+    tcg::mainloop<false>(ld, ld, ti * TILE, tj * TILE, kbeg, kend, ti == tj, c);    // chain bounded by kchunk (<= ~512)
+    const float* d = tcg::drain<false>(c, kend > kbeg);
     const float keep = 1.f - alpha;
     const int m0 = ti * TILE, c0 = tj * TILE;
     if (gridDim.y == 1) {
@@ -264,18 +264,21 @@ __global__ void seq_mean_kernel(const float* __restrict__ in, float* __restrict_
 // ---------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------
-static constexpr size_t kMaxPartialBytes = 256ull << 20;
+static constexpr size_t kMaxPartialBytes = 512ull << 20;
+
+constexpr long TC_MAX_KCHUNK = 512;      // tensor-core path: bounds the round-toward-zero TMEM accumulation chain
 
 static int choose_ksplit(int n, long K) {
     const int T = cdiv(n, TILE);
     const long tiles = (long)T * (T + 1) / 2;
     const long target = 3L * sm_count();            // ~3 waves of 2-CTA/SM
     long ks = target / tiles;
+    if (use_tc_gemm() && K >= 64) { const long need = (K + TC_MAX_KCHUNK - 1) / TC_MAX_KCHUNK; if (ks < need) ks = need; }
     const long max_by_k = (K + 4 * BK - 1) / (4 * BK);   // at least 4 slabs per split
     if (ks > max_by_k) ks = max_by_k;
     const long max_by_ws = (long)(kMaxPartialBytes / ((size_t)n * n * sizeof(float)));
     if (ks > max_by_ws) ks = max_by_ws;
-    if (ks > 512) ks = 512;
+    if (ks > 1024) ks = 1024;
     if (ks < 1) ks = 1;
     return (int)ks;
 }

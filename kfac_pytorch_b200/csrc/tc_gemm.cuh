@@ -27,11 +27,19 @@ constexpr int SMEM = 4 * PART;                           // A_hi, A_lo, B_hi, B_
 constexpr int DPITCH = TILE + 1;                         // drained accumulator pitch (floats)
 static_assert(SMEM >= TILE * DPITCH * 4, "drain buffer must fit in the operand buffers");
 
+// The tensor core accumulates into TMEM with round-toward-zero: a long chain of accumulations picks up a
+// systematic bias of ~3e-8 per UMMA K-step (measured: -1.4e-5 on the trace of a 2304-term product).  The
+// accumulator is therefore FLUSHED into fp32 registers (round-to-nearest adds) every FLUSH_SLABS k-slabs, which
+// bounds the in-TMEM chain to 32 K-steps (~1e-6) and makes the cross-chunk summation unbiased.
+constexpr int FLUSH_SLABS = 8;
+
 struct Ctx {
     unsigned char* dsm;
     uint64_t* mbar;
     uint32_t tmem;
     int slabs_done;       // slabs committed so far (mbarrier phase bookkeeping)
+    int flushed;          // 1 once acc[] holds flushed partial sums
+    float acc[64];        // this thread's share of the 128x128 tile (row 32*(warp&3)+lane, 64 columns)
 };
 
 // call at kernel start (all threads); `tmem_slot` and `mbar` live in static shared memory
@@ -41,7 +49,7 @@ __device__ __forceinline__ void setup(Ctx& c, unsigned char* dsm, uint64_t* mbar
     tc::tc_fence_before();
     __syncthreads();
     tc::tc_fence_after();
-    c.dsm = dsm; c.mbar = mbar; c.tmem = *tmem_slot; c.slabs_done = 0;
+    c.dsm = dsm; c.mbar = mbar; c.tmem = *tmem_slot; c.slabs_done = 0; c.flushed = 0;
 }
 __device__ __forceinline__ void teardown(Ctx& c) {
     tc::tc_fence_before();
@@ -92,8 +100,25 @@ __device__ __forceinline__ void stage(unsigned char* hi_base, unsigned char* lo_
     }
 }
 
-// accumulate over k in [kbeg, kend) into TMEM columns [0,128); returns when the accumulator is complete
-template <class LA, class LB>
+// add the TMEM accumulator into the register accumulator (all threads; the MMAs must have completed)
+__device__ __forceinline__ void flush_add(Ctx& c) {
+    const int warp = threadIdx.x >> 5;
+    const uint32_t taddr = c.tmem + ((uint32_t)(32 * (warp & 3)) << 16) + (warp >> 2) * 64;
+    float v[32];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        tc::tmem_ld32(taddr + 32 * h, v);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) c.acc[32 * h + i] = c.flushed ? c.acc[32 * h + i] + v[i] : v[i];
+    }
+    c.flushed = 1;
+    tc::tc_fence_before();        // ordered before the next __syncthreads / UMMA that overwrites the accumulator
+}
+
+// accumulate over k in [kbeg, kend) into TMEM columns [0,128) (+ the flushed registers); returns when complete
+// FLUSH = false: the caller bounds the chain itself (split-K chunks of <= 512 with an fp32 second stage) and
+// saves the 64 accumulator registers (3 CTAs / SM instead of 1).
+template <bool FLUSH, class LA, class LB>
 __device__ __forceinline__ void mainloop(const LA& la, const LB& lb, int m0, int n0, int kbeg, int kend,
                                          bool same_operand, Ctx& c) {
     unsigned char* a_hi = c.dsm;
@@ -104,8 +129,10 @@ __device__ __forceinline__ void mainloop(const LA& la, const LB& lb, int m0, int
     const int nslab = (kend - kbeg + BKS - 1) / BKS;
     if (nslab > 0) { fetch(la, m0, kbeg, ra); if (!same_operand) fetch(lb, n0, kbeg, rb); }
     constexpr uint32_t idesc = tc::idesc_tf32(128, 128, 0, 0);
+    int since = 0;                                           // slabs accumulated in TMEM since the last flush
     for (int s = 0; s < nslab; ++s) {
         if (c.slabs_done > 0) tc::mbar_wait(c.mbar, (uint32_t)((c.slabs_done - 1) & 1));   // smem free again
+        if (FLUSH && since == FLUSH_SLABS) { tc::tc_fence_after(); flush_add(c); since = 0; }
         stage<LA>(a_hi, a_lo, ra);
         if (!same_operand) stage<LB>(b_hi, b_lo, rb);
         if (s + 1 < nslab) {
@@ -126,18 +153,20 @@ __device__ __forceinline__ void mainloop(const LA& la, const LB& lb, int m0, int
                 for (int j = 0; j < BKS / 8; ++j) {
                     const uint64_t ad = tc::smem_desc(ab + 2 * j * LBO, LBO, SBO);
                     const uint64_t bd = tc::smem_desc(bb + 2 * j * LBO, LBO, SBO);
-                    tc::umma_tf32(c.tmem, ad, bd, idesc, !(s == 0 && pass == 0 && j == 0));
+                    tc::umma_tf32(c.tmem, ad, bd, idesc, !(since == 0 && pass == 0 && j == 0));
                 }
             }
             tc::umma_commit(c.mbar);
         }
         c.slabs_done += 1;
+        since += 1;
     }
     if (c.slabs_done > 0) tc::mbar_wait(c.mbar, (uint32_t)((c.slabs_done - 1) & 1));
     tc::tc_fence_after();
 }
 
 // TMEM accumulator (lane = m, column = n) -> shared memory float[128][DPITCH] (overwrites the operand buffers)
+template <bool FLUSH>
 __device__ __forceinline__ float* drain(Ctx& c, bool has_data) {
     float* d = reinterpret_cast<float*>(c.dsm);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -148,6 +177,10 @@ __device__ __forceinline__ float* drain(Ctx& c, bool has_data) {
     for (int h = 0; h < 2; ++h) {
         if (has_data) {
             tc::tmem_ld32(c.tmem + ((uint32_t)(32 * (warp & 3)) << 16) + cbase + 32 * h, v);
+            if (FLUSH && c.flushed) {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) v[i] += c.acc[32 * h + i];
+            }
         } else {
 #pragma unroll
             for (int i = 0; i < 32; ++i) v[i] = 0.f;
@@ -170,8 +203,8 @@ tc_gemm_kernel(LA la, LB lb, Epi epi, int M, int N, int K) {
     Ctx c;
     setup(c, dsm_raw, &mbar, &tmem_slot);
     const int m0 = blockIdx.y * TILE, n0 = blockIdx.x * TILE;
-    mainloop(la, lb, m0, n0, 0, K, false, c);
-    const float* d = drain(c, K > 0);
+    mainloop<true>(la, lb, m0, n0, 0, K, false, c);
+    const float* d = drain<true>(c, K > 0);
     for (int e = threadIdx.x; e < TILE * TILE; e += THREADS) {
         const int m = e >> 7, n = e & 127;
         if (m0 + m < M && n0 + n < N) epi(m0 + m, n0 + n, d[m * DPITCH + n]);
