@@ -1201,7 +1201,7 @@ extern "C" int kfacb_eigh_batched(const int32_t* n, int32_t count,
             LdKContig la{b.X + b.n_pad, 2L * b.n_pad, b.n, b.n};
             LdMnContig lb{b.A, (long)b.n, b.n, b.n};
             EpiToX epi{b.X, 2L * b.n_pad};
-            KFACB_CHECK_CUDA(launch_gemm_auto(la, lb, epi, b.n, b.n, b.n, gs));
+            KFACB_CHECK_CUDA(launch_gemm(la, lb, epi, b.n, b.n, b.n, gs));     // eigenvalues: exact fp32 FMAs (3xTF32 costs ~4e-6)
         }
         bj_rayleigh_kernel<<<dim3(cdiv(gp.nmax, 8), gp.nb), 256, 0, gs>>>(gr.dm);
         KFACB_CHECK_LAUNCH();
