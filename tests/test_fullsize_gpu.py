@@ -73,3 +73,56 @@ def test_inverse_vgg16_factor_size(eng):
     eye = torch.eye(n, device=DEV, dtype=torch.float64)
     assert ((iA.double() @ A.double()) - eye).abs().max().item() < 5e-4
     assert torch.equal(iA, iA.t())
+
+
+R50_LAYER_CLASSES = [
+    # (module ctor, input H=W, what)
+    (lambda: torch.nn.Conv2d(3, 64, 7, stride=2, padding=3, bias=False), 224, 'conv1 7x7 s2: dA=147, rows=401408'),
+    (lambda: torch.nn.Conv2d(64, 64, 3, padding=1, bias=False), 56, 'conv 3x3 @56: dA=576, rows=100352'),
+    (lambda: torch.nn.Conv2d(256, 512, 1, stride=2, bias=False), 56, 'downsample 1x1 s2: dA=256, dG=512'),
+    (lambda: torch.nn.Conv2d(512, 512, 3, padding=1, bias=False), 7, 'conv 3x3 @7: dA=4608, dG=512, rows=1568'),
+    (lambda: torch.nn.Linear(2048, 1000), None, 'fc: dA=2049, dG=1000, rows=32'),
+]
+
+
+@pytest.mark.parametrize('cls', R50_LAYER_CLASSES, ids=lambda c: c[2].split(':')[0].replace(' ', '_'))
+def test_resnet50_layer_step_vs_oracle_at_full_size(cls):
+    """Whole step() (factors -> eigh -> two-sided product -> KL clip) of ONE ResNet-50 layer at the BASELINE
+    batch size, 2 steps, against the oracle in fp64 (truth) and fp32 (the reference's own noise)."""
+    import kfac_pytorch_b200 as kfac
+    from kfac_pytorch_b200 import backend
+    from oracle.kfac_oracle import (OracleDPKFAC, specs_from_model, synth_grads, synth_layer_inputs)
+    ctor, hw, what = cls
+    backend.comm = None
+    torch.manual_seed(0)
+    mod = ctor()
+    model = torch.nn.Sequential(mod)
+    specs, mods = specs_from_model(model)
+    spec = specs[0]
+    hyper = dict(lr=0.0125, damping=0.002, kl_clip=0.001)
+    torch.set_num_threads(16)
+    res = {}
+    for tag, dt in (('f64', torch.float64), ('f32', torch.float32)):
+        orc_ = OracleDPKFAC([spec], variant='eigen_dp', **hyper)
+        for s in range(2):
+            gen = torch.Generator().manual_seed(100 + s)
+            li = synth_layer_inputs(spec, 32, None if hw is None else (hw, hw), None, gen, dt)
+            w, b = synth_grads(spec, gen, dt)
+            ow, ob = orc_.step([[li]], [w], [b])
+        res[tag] = ow[0].double()
+    model.to(DEV)
+    pre = kfac.get_kfac_module('eigen_dp')(model, hook_enabled=False, **hyper)
+    for s in range(2):
+        gen = torch.Generator().manual_seed(100 + s)
+        li = synth_layer_inputs(spec, 32, None if hw is None else (hw, hw), None, gen)
+        w, b = synth_grads(spec, gen)
+        pre.m_a[mod] = li.a.to(DEV); pre.m_g[mod] = li.g.to(DEV)
+        mod.weight.grad = w.to(DEV)
+        if b is not None:
+            mod.bias.grad = b.to(DEV)
+        pre.step()
+    ours = mod.weight.grad.double().cpu()
+    noise = ((res['f32'] - res['f64']).norm() / res['f64'].norm()).item()
+    err = ((ours - res['f64']).norm() / res['f64'].norm()).item()
+    print('\nFULLSIZE %-45s ours-vs-fp64 %.2e   reference-fp32-vs-fp64 %.2e' % (what, err, noise))
+    assert err <= max(1e-4, 3 * noise), (what, err, noise)
