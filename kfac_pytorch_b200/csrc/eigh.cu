@@ -706,7 +706,7 @@ bj_solve_kernel(const BjMat* mats, const int* pair_mat, BjState* state, int roun
 
 // end-of-round bookkeeping: sweep boundaries, convergence flags, active count for the host
 __global__ void bj_check_kernel(const BjMat* mats, BjState* state, int nmat, int round,
-                                int max_sweeps, volatile int* host_active) {
+                                int max_sweeps, volatile int* host_active, int one_sweep) {
     __shared__ int active;
     if (threadIdx.x == 0) active = 0;
     __syncthreads();
@@ -719,7 +719,7 @@ __global__ void bj_check_kernel(const BjMat* mats, BjState* state, int nmat, int
                 // off-block-diagonal norm seen DURING this sweep; Jacobi converges quadratically, so once
                 // it is below tol * ||A||_F the sweep just finished has pushed it to fp32 noise level.
                 const float tol = mats[mi].tol_conv;
-                if (st.off2 <= tol * tol * st.norm2 || st.sweeps >= max_sweeps) st.converged = 1;
+                if (one_sweep || st.off2 <= tol * tol * st.norm2 || st.sweeps >= max_sweeps) st.converged = 1;
                 st.off2 = 0.f;
                 state[mi] = st;
             }
@@ -809,6 +809,12 @@ __global__ void bj_write_kernel(const BjMat* mats) {
         const int r = r0 + rr, c = c0 + lx;
         if (r < mt.n && c < mt.n) mt.Q[(long)r * mt.n + c] = t[lx][rr];
     }
+}
+
+// re-arm every matrix of a group for the single clean-up sweep
+__global__ void bj_rearm_kernel(BjState* state, int nmat) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < nmat) { state[i].converged = 0; state[i].off2 = 0.f; }
 }
 
 __global__ void bj_store_sweeps_kernel(const BjState* state, const int* out_index, int nmat, int* sweeps_out) {
@@ -1158,7 +1164,7 @@ extern "C" int kfacb_eigh_batched(const int32_t* n, int32_t count,
             bool boundary = false;
             for (int a = 0; a < gp.nb && !boundary; ++a) boundary = ((r + 1) % (gr.hm[a].p - 1)) == 0;
             if (boundary) {
-                bj_check_kernel<<<1, 256, 0, gr.st>>>(gr.dm, gr.dstate, gp.nb, r, max_sweeps, rt->d_active + k);
+                bj_check_kernel<<<1, 256, 0, gr.st>>>(gr.dm, gr.dstate, gp.nb, r, max_sweeps, rt->d_active + k, 0);
                 count_launch(1);
             }
             count_launch(3);
@@ -1181,7 +1187,11 @@ extern "C" int kfacb_eigh_batched(const int32_t* n, int32_t count,
         GroupRun& gr = run[k];
         const GroupPlan& gp = *gr.gp;
         cudaStream_t gs = gr.st;
-        // one Newton-Schulz step removes the orthogonality drift of ~1e3 accumulated fp32 rotations
+        // Clean-up.  ~1e3 rounds of 3xTF32 row updates leave V slightly non-orthogonal and W = A V slightly
+        // inconsistent (the tensor core accumulates round-toward-zero: a biased drift of ~4e-4 in the row norms),
+        // which would cap the accuracy at ~1e-4.  So: (a) one Newton-Schulz step re-orthogonalises V,
+        // (b) W is recomputed from scratch as A V, (c) ONE more Jacobi sweep on the now consistent pair removes
+        // what is left (quadratically), with only one sweep's worth of fresh rounding.
         if (env_int("KFACB_NS", 1)) {
             for (int a = 0; a < gp.nb; ++a) {
                 const BjMat& b = gr.hm[a];
@@ -1194,6 +1204,29 @@ extern "C" int kfacb_eigh_batched(const int32_t* n, int32_t count,
                 KFACB_CHECK_CUDA(cudaMemcpy2DAsync(b.X + b.n_pad, ld * sizeof(float), b.Q, (size_t)b.n * sizeof(float),
                                                    (size_t)b.n * sizeof(float), b.n, cudaMemcpyDeviceToDevice, gs));
             }
+        }
+        if (env_int("KFACB_CLEANUP_SWEEP", 1) && !prof) {
+            int pmax = 0;
+            for (int a = 0; a < gp.nb; ++a) {
+                const BjMat& b = gr.hm[a];
+                if (b.p > pmax) pmax = b.p;
+                LdKContig la{b.X + b.n_pad, 2L * b.n_pad, b.n, b.n};       // W^T rows = (A v_i)^T = v_i^T A
+                LdMnContig lb{b.A, (long)b.n, b.n, b.n};
+                KFACB_CHECK_CUDA(launch_gemm_auto(la, lb, EpiToX{b.X, 2L * b.n_pad}, b.n, b.n, b.n, gs));
+            }
+            bj_rearm_kernel<<<cdiv(gp.nb, 128), 128, 0, gs>>>(gr.dstate, gp.nb);
+            KFACB_CHECK_LAUNCH();
+            const int col_tiles = cdiv(gp.max_ld, TILE);
+            for (int r = 0; r < pmax - 1; ++r) {
+                bj_h_tc_kernel<<<dim3(gp.max_ksplit, gp.total_pairs), tcg::THREADS, tcg::SMEM, gs>>>(gr.dm, gr.dpm, gr.dstate, r, gr.partial, gr.dpoff);
+                bj_solve_kernel<<<gp.total_pairs, SOLVE_THREADS, SOLVE_SMEM, gs>>>(gr.dm, gr.dpm, gr.dstate, r, gr.partial, gr.dpoff, gr.ubuf, inner_sweeps, full_inner);
+                bj_update_tc_kernel<<<dim3(cdiv(col_tiles, upd_g), gp.total_pairs), UPD_THREADS, UPD_SMEM, gs>>>(gr.dm, gr.dpm, gr.dstate, r, gr.ubuf, upd_g);
+                bool boundary = false;
+                for (int a = 0; a < gp.nb && !boundary; ++a) boundary = ((r + 1) % (gr.hm[a].p - 1)) == 0;
+                if (boundary) { bj_check_kernel<<<1, 256, 0, gs>>>(gr.dm, gr.dstate, gp.nb, r, max_sweeps, rt->d_active + k, 1); count_launch(1); }
+                count_launch(3);
+            }
+            KFACB_CHECK_LAUNCH();
         }
         // Rayleigh quotients: Y = V^T A  (row i of Y = A v_i), written over the W half
         for (int a = 0; a < gp.nb; ++a) {
