@@ -194,7 +194,9 @@ __device__ __forceinline__ float* drain(Ctx& c, bool has_data) {
 }
 
 // generic GEMM: C(m, n) = epi(m, n, sum_k A(m,k) B(n,k)); grid (tiles_n, tiles_m)
-template <class LA, class LB, class Epi>
+// FLUSH is chosen by the host from K: products with K <= 512 keep the chain short anyway and run the
+// register-lean variant (3 CTAs / SM).
+template <class LA, class LB, class Epi, bool FLUSH>
 __global__ void __launch_bounds__(THREADS)
 tc_gemm_kernel(LA la, LB lb, Epi epi, int M, int N, int K) {
     extern __shared__ __align__(128) unsigned char dsm_raw[];
@@ -203,8 +205,8 @@ tc_gemm_kernel(LA la, LB lb, Epi epi, int M, int N, int K) {
     Ctx c;
     setup(c, dsm_raw, &mbar, &tmem_slot);
     const int m0 = blockIdx.y * TILE, n0 = blockIdx.x * TILE;
-    mainloop<true>(la, lb, m0, n0, 0, K, false, c);
-    const float* d = drain<true>(c, K > 0);
+    mainloop<FLUSH>(la, lb, m0, n0, 0, K, false, c);
+    const float* d = drain<FLUSH>(c, K > 0);
     for (int e = threadIdx.x; e < TILE * TILE; e += THREADS) {
         const int m = e >> 7, n = e & 127;
         if (m0 + m < M && n0 + n < N) epi(m0 + m, n0 + n, d[m * DPITCH + n]);
@@ -212,18 +214,23 @@ tc_gemm_kernel(LA la, LB lb, Epi epi, int M, int N, int K) {
     teardown(c);
 }
 
-template <class LA, class LB, class Epi>
-static inline cudaError_t launch(const LA& la, const LB& lb, const Epi& epi, int M, int N, int K, cudaStream_t st) {
+template <class LA, class LB, class Epi, bool FLUSH>
+static inline cudaError_t launch_variant(const LA& la, const LB& lb, const Epi& epi, int M, int N, int K, cudaStream_t st) {
     static bool attr_done = false;       // per template instantiation
     if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(tc_gemm_kernel<LA, LB, Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+        cudaError_t e = cudaFuncSetAttribute(tc_gemm_kernel<LA, LB, Epi, FLUSH>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
         if (e != cudaSuccess) return e;
         attr_done = true;
     }
     dim3 grid(cdiv(N, TILE), cdiv(M, TILE));
-    tc_gemm_kernel<LA, LB, Epi><<<grid, THREADS, SMEM, st>>>(la, lb, epi, M, N, K);
+    tc_gemm_kernel<LA, LB, Epi, FLUSH><<<grid, THREADS, SMEM, st>>>(la, lb, epi, M, N, K);
     count_launch();
     return cudaGetLastError();
+}
+template <class LA, class LB, class Epi>
+static inline cudaError_t launch(const LA& la, const LB& lb, const Epi& epi, int M, int N, int K, cudaStream_t st) {
+    if (K > FLUSH_SLABS * BKS * 2) return launch_variant<LA, LB, Epi, true>(la, lb, epi, M, N, K, st);
+    return launch_variant<LA, LB, Epi, false>(la, lb, epi, M, N, K, st);
 }
 
 }  // namespace tcg
