@@ -1,9 +1,10 @@
 """kfac_pytorch_b200 -- B200-native (sm_100a) DP-KFAC gradient preconditioner.
 
-Drop-in for the ``kfac`` package of lzhangbv/kfac_pytorch on the
-distributed-preconditioning path: same ``get_kfac_module`` / ``kfac_mappers`` /
-``DP_KFAC`` / ``KFACParamScheduler`` / ``backend`` surface
-(kfac/__init__.py:1-16, kfac/dp_kfac.py:4-40), CUDA kernels underneath.
+Drop-in for the ``kfac`` package of lzhangbv/kfac_pytorch: same ``get_kfac_module`` /
+``kfac_mappers`` (``inverse``, ``eigen``, ``inverse_dp``, ``eigen_dp``) / ``DP_KFAC`` /
+``KFACParamScheduler`` / ``backend`` surface (kfac/__init__.py:1-16, kfac/dp_kfac.py:4-40),
+CUDA kernels underneath.  The distributed-preconditioning variants are the hot path this
+package is built and benchmarked for.
 """
 from . import backend
 from .preconditioner import KFAC_EIGEN, KFAC_EIGEN_DP, KFAC_INV, KFAC_INV_DP

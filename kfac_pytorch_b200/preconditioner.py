@@ -1,7 +1,11 @@
-"""Host side of the B200-native DP-KFAC preconditioner.
+"""Host side of the B200-native K-FAC preconditioner.
 
-Mirrors the reference's Python surface for the distributed-preconditioning
-variants (``eigen_dp`` / ``inverse_dp``):
+Mirrors the reference's Python surface.  The hot path this package is built
+for is the distributed-preconditioning pair (``eigen_dp`` / ``inverse_dp``);
+the model-parallel variants (``eigen`` / ``inverse``: full factor replicas +
+all-reduce + distributed inverse, kfac_preconditioner_eigen.py /
+kfac_preconditioner_inv.py) run on the same kernels with a different
+communication schedule.
 
   reference                                           here
   --------------------------------------------------  ---------------------------
@@ -101,20 +105,26 @@ class KFAC(optim.Optimizer):
     reference default, or 'greedy' = longest-processing-time on dA^3+dG^3) is
     keyword-only and not part of the reference signature.
     """
-    variant = None   # 'eigen_dp' | 'inverse_dp'
+    variant = None   # 'eigen_dp' | 'inverse_dp' (distributed preconditioning) | 'eigen' | 'inverse' (MPD)
 
     def __init__(self, model, lr=0.1, damping=0.001, fac_update_freq=1, kfac_update_freq=1,
                  kl_clip=0.001, factor_decay=0.95, exclude_vocabulary_size=None,
-                 hook_enabled=True, exclude_parts='', *, partition='round_robin', engine=None):
+                 hook_enabled=True, exclude_parts='', *, partition='round_robin', engine=None,
+                 communicate_inverse_or_not=False, distribute_layer_factors=None):
         defaults = dict(lr=lr, damping=damping, fac_update_freq=fac_update_freq,
                         kfac_update_freq=kfac_update_freq)
         super().__init__(model.parameters(), defaults)
-        if self.variant not in ('eigen_dp', 'inverse_dp'):
-            raise NotImplementedError('use KFAC_EIGEN_DP / KFAC_INV_DP (or kfac.get_kfac_module)')
+        if self.variant not in ('eigen_dp', 'inverse_dp', 'eigen', 'inverse'):
+            raise NotImplementedError('use kfac.get_kfac_module(...) / the KFAC_* classes')
         backend.ensure_initialized()
+        self.is_dp = self.variant.endswith('_dp')
+        self.uses_eigen = self.variant.startswith('eigen')
         self.fac_update_freq = fac_update_freq
         self.kfac_update_freq = kfac_update_freq
-        self.communicate_inverse_or_not = False          # DP variants always exchange preconditioned grads
+        # DP variants always exchange preconditioned grads (inv_dp.py:49); MPD eigen always exchanges the
+        # eigenbases (eigen.py:53); MPD inverse takes the flag from its constructor (inv.py:42)
+        self.communicate_inverse_or_not = (False if self.is_dp else
+                                           (True if self.variant == 'eigen' else bool(communicate_inverse_or_not)))
         self.kl_clip = kl_clip if (kl_clip is not None and kl_clip > 0) else None
         self.factor_decay = factor_decay
         self.exclude_vocabulary_size = exclude_vocabulary_size
@@ -144,7 +154,14 @@ class KFAC(optim.Optimizer):
         self._slab = None
         self._slab_segments = None
         self._nu = None
-        self.schedule_module_ranks()       # DP variants schedule eagerly (inv_dp.py:57)
+        # factor-wise distribution of the MPD eigen variant (eigen.py:66-71)
+        if distribute_layer_factors is None:
+            self.distribute_layer_factors = (self.variant == 'eigen' and
+                                             backend.comm.size() > len(self.modules))
+        else:
+            self.distribute_layer_factors = bool(distribute_layer_factors) and self.variant == 'eigen'
+        if self.is_dp:
+            self.schedule_module_ranks()   # DP variants schedule eagerly (inv_dp.py:57)
 
     # ------------------------------------------------------------------ hooks
     def set_hook_enabled(self, mode=True):
@@ -153,6 +170,9 @@ class KFAC(optim.Optimizer):
     def _forward_hook_event(self, module, input):
         """Owner-only capture of the layer input (kfac_preconditioner_inv_dp.py:60-65)."""
         if self.hook_enabled and torch.is_grad_enabled() and self.steps % self.fac_update_freq == 0:
+            if not self.is_dp:                     # MPD: every rank keeps its local batch (base.py:122-125)
+                self.m_a[module] = input[0].data
+                return
             rank_a, _ = self.module_ranks[module]
             if backend.comm.rank() == rank_a:
                 self.m_a[module] = input[0].data
@@ -160,6 +180,9 @@ class KFAC(optim.Optimizer):
     def _backward_hook_event(self, module, grad_input, grad_output):
         """Owner-only capture of the output gradient (kfac_preconditioner_inv_dp.py:67-72)."""
         if self.hook_enabled and self.steps % self.fac_update_freq == 0:
+            if not self.is_dp:                     # MPD (base.py:127-130)
+                self.m_g[module] = grad_output[0].data
+                return
             _, rank_g = self.module_ranks[module]
             if backend.comm.rank() == rank_g:
                 self.m_g[module] = grad_output[0].data
@@ -201,8 +224,16 @@ class KFAC(optim.Optimizer):
                 ranks[self.modules[i]] = (r, r)
             ranks = {m: ranks[m] for m in self.modules}
         elif self.partition in ('round_robin', 'greedy'):
-            for i, module in enumerate(self.modules):
-                ranks[module] = (i % size, i % size)
+            it = 0
+            for module in self.modules:
+                rank_a = it % size
+                if self.distribute_layer_factors:  # factor-wise: G on the next rank (eigen.py:82-90)
+                    it += 1
+                    rank_g = it % size
+                else:
+                    rank_g = rank_a
+                ranks[module] = (rank_a, rank_g)
+                it += 1
         else:
             raise ValueError('unknown partition %r' % (self.partition,))
         self.module_ranks = ranks
@@ -233,7 +264,7 @@ class KFAC(optim.Optimizer):
         """A/G accumulation + running average on the owner only, from the owner's
         local mini-batch (kfac_preconditioner_inv_dp.py:75-90)."""
         eng = self._get_engine()
-        owned = self._owned()
+        owned = self._owned() if self.is_dp else list(range(len(self.modules)))   # MPD: full replicas (inv.py:80-91)
         if not owned:
             return
         descs, a_l, g_l, A_l, G_l = [], [], [], [], []
@@ -249,37 +280,81 @@ class KFAC(optim.Optimizer):
         eng.factor_update(descs, a_l, g_l, A_l, G_l, self.factor_decay, self.steps == 0)
 
     def _communicate_factors(self):
-        """No factor communication in the DP variants (kfac_preconditioner_inv_dp.py:93-95)."""
-        pass
+        """DP: no factor communication (kfac_preconditioner_inv_dp.py:93-95).
+        MPD: average-all-reduce of every factor (kfac_preconditioner_inv.py:94-103)."""
+        if self.is_dp:
+            return
+        handles = []
+        for m in self.modules:
+            handles.append(backend.comm.allreduce_async_(self.m_A[m], op=backend.comm.Average))
+            handles.append(backend.comm.allreduce_async_(self.m_G[m], op=backend.comm.Average))
+        for h in handles:
+            backend.comm.synchronize(h)
 
     # ---------------------------------------------------------------- phase 2
     def _compute_inverse(self):
         eng = self._get_engine()
-        owned = self._owned()
-        if not owned:
-            return
-        if self.variant == 'eigen_dp':
-            # eigh + floor on the owner (kfac_preconditioner_eigen_dp.py:62-75)
+        me = backend.comm.rank()
+        if self.uses_eigen:
+            # eigh + floor on the owner of each factor (eigen_dp.py:62-75; MPD eigen.py:98-119, where the A and
+            # G factor of a layer may live on different ranks and non-owners start from zeros)
             mats, Qs, ds = [], [], []
-            for i in owned:
-                m = self.modules[i]
-                A, G = self.m_A[m], self.m_G[m]
+            for i, m in enumerate(self.modules):
+                rank_a, rank_g = self.module_ranks[m]
+                own_a, own_g = me == rank_a, me == rank_g
+                if self.is_dp and not own_a:
+                    continue
+                A, G = self.m_A.get(m), self.m_G.get(m)
                 if m not in self.m_QA:
-                    self.m_QA[m] = torch.empty_like(A); self.m_dA[m] = A.new_empty(A.shape[0])
-                    self.m_QG[m] = torch.empty_like(G); self.m_dG[m] = G.new_empty(G.shape[0])
-                mats += [A, G]; Qs += [self.m_QA[m], self.m_QG[m]]; ds += [self.m_dA[m], self.m_dG[m]]
-            eng.eigh(mats, Qs, ds, self.eps)
+                    da, dg = self._static[i].dA, self._static[i].dG
+                    dev = self._device()
+                    mk = torch.empty if self.is_dp else torch.zeros
+                    self.m_QA[m] = mk(da, da, dtype=torch.float32, device=dev)
+                    self.m_dA[m] = mk(da, dtype=torch.float32, device=dev)
+                    self.m_QG[m] = mk(dg, dg, dtype=torch.float32, device=dev)
+                    self.m_dG[m] = mk(dg, dtype=torch.float32, device=dev)
+                if own_a:
+                    mats.append(A); Qs.append(self.m_QA[m]); ds.append(self.m_dA[m])
+                if own_g:
+                    mats.append(G); Qs.append(self.m_QG[m]); ds.append(self.m_dG[m])
+            if mats:
+                eng.eigh(mats, Qs, ds, self.eps)
         else:
-            # pi-damped (in place!) Cholesky-equivalent inverse (kfac_preconditioner_inv_dp.py:98-123)
+            # pi-damped (in place, on the owner's copy only!) Cholesky-equivalent inverse
+            # (inv_dp.py:98-123; MPD inv.py:109-129, where non-owners keep zero inverses)
             A_l, G_l, iA, iG = [], [], [], []
-            for i in owned:
-                m = self.modules[i]
-                A, G = self.m_A[m], self.m_G[m]
+            for i, m in enumerate(self.modules):
+                rank_a, rank_g = self.module_ranks[m]
+                assert rank_a == rank_g
+                own = me == rank_a
+                if self.is_dp and not own:
+                    continue
                 if m not in self.m_inv_A:
-                    self.m_inv_A[m] = torch.empty_like(A)
-                    self.m_inv_G[m] = torch.empty_like(G)
-                A_l.append(A); G_l.append(G); iA.append(self.m_inv_A[m]); iG.append(self.m_inv_G[m])
-            eng.pi_damped_inverse(A_l, G_l, iA, iG, self.damping)
+                    mk = torch.empty_like if self.is_dp else torch.zeros_like
+                    self.m_inv_A[m] = mk(self.m_A[m])
+                    self.m_inv_G[m] = mk(self.m_G[m])
+                if own:
+                    A_l.append(self.m_A[m]); G_l.append(self.m_G[m])
+                    iA.append(self.m_inv_A[m]); iG.append(self.m_inv_G[m])
+            if A_l:
+                eng.pi_damped_inverse(A_l, G_l, iA, iG, self.damping)
+
+    def _communicate_inverse(self):
+        """MPD only: broadcast the inverses / eigenbases from their owners
+        (kfac_preconditioner_inv.py:132-142, kfac_preconditioner_eigen.py:122-134)."""
+        handles = []
+        for m in self.modules:
+            rank_a, rank_g = self.module_ranks[m]
+            if self.uses_eigen:
+                handles.append(backend.comm.broadcast_async_(self.m_QA[m], rank_a))
+                handles.append(backend.comm.broadcast_async_(self.m_dA[m], rank_a))
+                handles.append(backend.comm.broadcast_async_(self.m_QG[m], rank_g))
+                handles.append(backend.comm.broadcast_async_(self.m_dG[m], rank_g))
+            else:
+                handles.append(backend.comm.broadcast_async_(self.m_inv_A[m], rank_a))
+                handles.append(backend.comm.broadcast_async_(self.m_inv_G[m], rank_g))
+        for h in handles:
+            backend.comm.synchronize(h)
 
     # ---------------------------------------------------------------- phase 3
     def _ensure_slab(self):
@@ -324,17 +399,18 @@ class KFAC(optim.Optimizer):
 
     def _compute_pred(self):
         """Owner-only two-sided product (eigen_dp.py:78-93 / inv_dp.py:126-138)."""
-        assert not self.communicate_inverse_or_not
         eng = self._get_engine()
         self._ensure_slab()
-        owned = self._owned()
+        # DP: owner only.  MPD: every rank multiplies every layer with whatever inverse it holds
+        # (zeros on non-owners unless the inverses were broadcast; inv.py:156-161, eigen.py:137-144)
+        owned = self._owned() if self.is_dp else list(range(len(self.modules)))
         if not owned:
             return
         descs = [self._static[i] for i in owned]
         w, b = self._grads(owned)
         out = [self.m_precon_grad[self.modules[i]] for i in owned]
         mods = [self.modules[i] for i in owned]
-        if self.variant == 'eigen_dp':
+        if self.uses_eigen:
             eng.precond_eigen(descs, [self.m_QA[m] for m in mods], [self.m_QG[m] for m in mods],
                               [self.m_dA[m] for m in mods], [self.m_dG[m] for m in mods],
                               w, b, out, self.damping)
@@ -365,6 +441,29 @@ class KFAC(optim.Optimizer):
                      float(self.lr), self.kl_clip,
                      self.kl_clip is not None and self.exclude_communicate_inverse, self._nu)
 
+    # ------------------------------------------------------ K-FAC state (resume)
+    def kfac_state_dict(self):
+        """Factors, inverses / eigenbases and the step counter, keyed by module index.  The reference keeps this
+        state in plain dicts outside ``Optimizer.state`` and silently loses it on resume
+        (SURVEY.md section 5 / 8f rank 4); ``torch.save`` this next to ``state_dict()``."""
+        def pack(d):
+            return {i: d[m].detach().to("cpu", copy=True) for i, m in enumerate(self.modules) if m in d}
+        return dict(variant=self.variant, steps=self.steps, world_size=backend.comm.size(),
+                    m_A=pack(self.m_A), m_G=pack(self.m_G), m_QA=pack(self.m_QA), m_QG=pack(self.m_QG),
+                    m_dA=pack(self.m_dA), m_dG=pack(self.m_dG), m_inv_A=pack(self.m_inv_A),
+                    m_inv_G=pack(self.m_inv_G))
+
+    def load_kfac_state_dict(self, state):
+        if state['variant'] != self.variant or state['world_size'] != backend.comm.size():
+            raise ValueError('K-FAC state was saved for variant=%s world_size=%d' % (state['variant'], state['world_size']))
+        dev = self._device()
+        for name in ('m_A', 'm_G', 'm_QA', 'm_QG', 'm_dA', 'm_dG', 'm_inv_A', 'm_inv_G'):
+            tgt = getattr(self, name)
+            tgt.clear()
+            for i, t in state[name].items():
+                tgt[self.modules[int(i)]] = t.to(dev).contiguous()
+        self.steps = int(state['steps'])
+
     # ------------------------------------------------------------------- step
     @torch.no_grad()
     def step(self, closure=None, epoch=None):
@@ -389,6 +488,9 @@ class KFAC(optim.Optimizer):
         if self.steps % self.kfac_update_freq == 0:
             if not self.exclude_compute_inverse:
                 self._compute_inverse()
+            if not self.exclude_communicate_inverse and self.communicate_inverse_or_not:
+                if backend.comm.size() > 1:
+                    self._communicate_inverse()
 
         if not self.exclude_compute_inverse:
             self._compute_pred()
@@ -415,22 +517,33 @@ class KFAC_INV_DP(KFAC):
     variant = 'inverse_dp'
 
 
-class _MPDUnsupported(KFAC):
-    """The model-parallel ('MPD') variants ``inverse`` / ``eigen`` of the reference
-    (kfac_preconditioner_inv.py / kfac_preconditioner_eigen.py: factor all-reduce +
-    inverse broadcast) are outside the hot path this package accelerates
-    (SURVEY.md section 8f rank 3).  The keys exist so ``kfac_mappers.keys()`` matches."""
-    variant = None
+class KFAC_INV(KFAC):
+    """``inverse`` (MPD-KFAC, explicit inverse): kfac/kfac_preconditioner_inv.py.  Full factor replicas
+    averaged with an all-reduce, owner-only damped inverse, then either the preconditioned gradients
+    (default) or the inverses are broadcast.  Same constructor order as the reference (:35-45)."""
+    variant = 'inverse'
 
-    def __init__(self, *args, **kwargs):
-        raise NotImplementedError(
-            "kfac_pytorch_b200 implements the distributed-preconditioning variants "
-            "'eigen_dp' and 'inverse_dp' only; '%s' (MPD-KFAC) is not provided" % self._name)
+    def __init__(self, model, lr=0.1, damping=0.001, fac_update_freq=1, kfac_update_freq=1,
+                 communicate_inverse_or_not=False, kl_clip=0.001, factor_decay=0.95,
+                 exclude_vocabulary_size=None, hook_enabled=True, exclude_parts='', **kw):
+        super().__init__(model, lr=lr, damping=damping, fac_update_freq=fac_update_freq,
+                         kfac_update_freq=kfac_update_freq, kl_clip=kl_clip, factor_decay=factor_decay,
+                         exclude_vocabulary_size=exclude_vocabulary_size, hook_enabled=hook_enabled,
+                         exclude_parts=exclude_parts,
+                         communicate_inverse_or_not=communicate_inverse_or_not, **kw)
 
 
-class KFAC_INV(_MPDUnsupported):
-    _name = 'inverse'
+class KFAC_EIGEN(KFAC):
+    """``eigen`` (MPD-KFAC with eigendecomposition, SC'20): kfac/kfac_preconditioner_eigen.py.  Full factor
+    replicas + all-reduce, distributed eigh (optionally factor-wise), broadcast of (Q, d), every rank
+    preconditions.  Same constructor order as the reference (:36-46)."""
+    variant = 'eigen'
 
-
-class KFAC_EIGEN(_MPDUnsupported):
-    _name = 'eigen'
+    def __init__(self, model, lr=0.1, damping=0.001, fac_update_freq=1, kfac_update_freq=1,
+                 distribute_layer_factors=None, kl_clip=0.001, factor_decay=0.95,
+                 exclude_vocabulary_size=None, hook_enabled=True, exclude_parts='', **kw):
+        super().__init__(model, lr=lr, damping=damping, fac_update_freq=fac_update_freq,
+                         kfac_update_freq=kfac_update_freq, kl_clip=kl_clip, factor_decay=factor_decay,
+                         exclude_vocabulary_size=exclude_vocabulary_size, hook_enabled=hook_enabled,
+                         exclude_parts=exclude_parts,
+                         distribute_layer_factors=distribute_layer_factors, **kw)

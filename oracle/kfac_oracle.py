@@ -345,6 +345,115 @@ class OracleDPKFAC:
         return out_w, out_b
 
 
+class OracleMPDKFAC:
+    """Restatement of the two model-parallel ("MPD") variants -- ``inverse``
+    (kfac_preconditioner_inv.py) and ``eigen`` (kfac_preconditioner_eigen.py) -- simulating ``world_size``
+    ranks in one process.  Unlike the DP variants every rank keeps its OWN copy of every factor:
+
+      (1) each rank accumulates A/G from its local batch into its copy (identity init + EMA, inv.py:80-91);
+      (2) the copies are averaged across ranks in place (all-reduce, inv.py:94-103);
+      (3) ``inverse``: pi from the averaged factors, then ONLY the owner adds sqrt(damping)*pi to ITS copy (the
+          in-place add of inv.py:122-128 runs under the rank guard, so the replicas drift apart until the next
+          average) and inverts; ``eigen``: the owner of each factor (rank_a for A, rank_g for G) runs eigh + floor
+          (eigen.py:98-119);
+      (4) ``eigen`` broadcasts (Q, d) and every rank preconditions (eigen.py:122-144); ``inverse`` either
+          broadcasts the inverses (communicate_inverse_or_not=True) or lets the owner precondition and broadcasts
+          the result (default, inv.py:156-175) -- all ranks end with the owner's numbers either way;
+      (5) KL clip as in the DP variants (inv.py:188-217).
+    """
+
+    def __init__(self, specs: Sequence[LayerSpec], variant: str = 'eigen', lr: float = 0.1,
+                 damping: float = 0.001, fac_update_freq: int = 1, kfac_update_freq: int = 1,
+                 kl_clip: Optional[float] = 0.001, factor_decay: float = 0.95, world_size: int = 1,
+                 distribute_layer_factors: Optional[bool] = None):
+        assert variant in ('eigen', 'inverse')
+        self.specs = list(specs)
+        self.variant = variant
+        self.lr, self.damping = lr, damping
+        self.fac_update_freq, self.kfac_update_freq = fac_update_freq, kfac_update_freq
+        self.kl_clip = kl_clip if (kl_clip is not None and kl_clip > 0) else None
+        self.factor_decay = factor_decay
+        self.world_size = world_size
+        if distribute_layer_factors is None:                       # eigen.py:66-71
+            distribute_layer_factors = variant == 'eigen' and world_size > len(self.specs)
+        self.owner_a, self.owner_g = [], []
+        it = 0
+        for _ in self.specs:                                       # eigen.py:75-94 / inv.py:62-77
+            ra = it % world_size
+            if distribute_layer_factors and variant == 'eigen':
+                it += 1
+                rg = it % world_size
+            else:
+                rg = ra
+            self.owner_a.append(ra); self.owner_g.append(rg)
+            it += 1
+        self.owners = self.owner_a
+        self.eps = 1e-10
+        self.steps = 0
+        n = len(self.specs)
+        self.m_A = [[None] * n for _ in range(world_size)]          # [rank][layer]
+        self.m_G = [[None] * n for _ in range(world_size)]
+        self.m_QA = [None] * n; self.m_QG = [None] * n
+        self.m_dA = [None] * n; self.m_dG = [None] * n
+        self.m_inv_A = [None] * n; self.m_inv_G = [None] * n
+        self.m_precon = [None] * n
+        self.last_nu = 1.0
+
+    def step(self, per_rank_inputs, wgrads, bgrads, lr=None, damping=None):
+        if lr is not None:
+            self.lr = lr
+        if damping is not None:
+            self.damping = damping
+        P = self.world_size
+        if self.steps % self.fac_update_freq == 0:
+            for l, spec in enumerate(self.specs):
+                for r in range(P):
+                    li = per_rank_inputs[r][l]
+                    A_new = factor_A(li.a, spec)
+                    G_new = factor_G(li.g, spec, batch_averaged=True)
+                    if self.steps == 0:
+                        self.m_A[r][l] = torch.eye(A_new.shape[0], dtype=A_new.dtype)
+                        self.m_G[r][l] = torch.eye(G_new.shape[0], dtype=G_new.dtype)
+                    self.m_A[r][l] = running_average(A_new, self.m_A[r][l], self.factor_decay)
+                    self.m_G[r][l] = running_average(G_new, self.m_G[r][l], self.factor_decay)
+                if P > 1:                                           # sum over ranks, then divide (backend.py:136-139)
+                    A_avg = sum(self.m_A[r][l] for r in range(P)) / P
+                    G_avg = sum(self.m_G[r][l] for r in range(P)) / P
+                    for r in range(P):
+                        self.m_A[r][l] = A_avg.clone()
+                        self.m_G[r][l] = G_avg.clone()
+        if self.steps % self.kfac_update_freq == 0:
+            for l in range(len(self.specs)):
+                ra, rg = self.owner_a[l], self.owner_g[l]
+                if self.variant == 'eigen':
+                    self.m_dA[l], self.m_QA[l] = eig_floored(self.m_A[ra][l], self.eps)
+                    self.m_dG[l], self.m_QG[l] = eig_floored(self.m_G[rg][l], self.eps)
+                else:
+                    A, G = self.m_A[ra][l], self.m_G[ra][l]
+                    (self.m_A[ra][l], self.m_G[ra][l],
+                     self.m_inv_A[l], self.m_inv_G[l]) = pi_damped_inverses(A, G, self.damping)
+        v_all, g_all, out_w, out_b = [], [], [], []
+        for l, spec in enumerate(self.specs):
+            gm = grad_matrix(spec, wgrads[l], bgrads[l])
+            if self.variant == 'eigen':
+                v = precondition_eigen(gm, self.m_QA[l], self.m_dA[l], self.m_QG[l], self.m_dG[l], self.damping)
+            else:
+                v = precondition_inverse(gm, self.m_inv_A[l], self.m_inv_G[l])
+            self.m_precon[l] = v
+            vw, vb = split_preconditioned(
+                spec, v, wgrads[l].shape, None if bgrads[l] is None else bgrads[l].shape)
+            v_all.append(vw); g_all.append(wgrads[l])
+            if vb is not None:
+                v_all.append(vb); g_all.append(bgrads[l])
+            out_w.append(vw); out_b.append(vb)
+        nu = kl_clip_scale(v_all, g_all, self.lr, self.kl_clip)
+        self.last_nu = nu
+        out_w = [w * nu for w in out_w]
+        out_b = [None if b is None else b * nu for b in out_b]
+        self.steps += 1
+        return out_w, out_b
+
+
 # --------------------------------------------------------------------------
 # seeded synthetic inputs shared by the golden generator, the tests and bench
 # --------------------------------------------------------------------------

@@ -38,6 +38,7 @@ class Case:
     world_size: int = 1
     seed: int = 1234
     lr_schedule: Optional[List[float]] = None  # per-step lr written to param_groups[0]
+    extra: dict = field(default_factory=dict)   # variant-specific constructor kwargs (e.g. distribute_layer_factors)
 
 
 class Flatten(nn.Module):
@@ -98,6 +99,16 @@ CASES = [
          kl_clip=None, damping=0.03),
     Case('mlp_small_eigen_ws2', 'eigen_dp', mlp_small, batch=8, steps=3, world_size=2),
     Case('convnet_bias_inverse_ws2', 'inverse_dp', convnet_bias, batch=6, steps=2, hw=(8, 8),
+         damping=0.03, world_size=2),
+    # model-parallel ("MPD") variants: full factor replicas + all-reduce
+    Case('mlp_small_inverse_mpd_ws2', 'inverse', mlp_small, batch=8, steps=3, world_size=2),
+    Case('mlp_small_eigen_mpd_ws2', 'eigen', mlp_small, batch=8, steps=3, world_size=2),
+    Case('convnet_bias_eigen_mpd', 'eigen', convnet_bias, batch=6, steps=2, hw=(8, 8)),
+    Case('mlp_small_eigen_mpd_factorwise_ws2', 'eigen', mlp_small, batch=8, steps=2, world_size=2,
+         extra=dict(distribute_layer_factors=True)),
+    Case('mlp_small_inverse_mpd_comminv_ws2', 'inverse', mlp_small, batch=8, steps=2, world_size=2,
+         extra=dict(communicate_inverse_or_not=True)),
+    Case('convnet_bias_inverse_mpd_ws2', 'inverse', convnet_bias, batch=6, steps=2, hw=(8, 8),
          damping=0.03, world_size=2),
 ]
 CASES_BY_NAME = {c.name: c for c in CASES}

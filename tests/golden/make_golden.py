@@ -64,8 +64,11 @@ def _run_case(case, rank, world_size, dtype, port):
     KFAC = kfac.get_kfac_module(case.variant)
     pre = KFAC(model, lr=case.lr, damping=case.damping, fac_update_freq=case.fac_update_freq,
                kfac_update_freq=case.kfac_update_freq, kl_clip=case.kl_clip,
-               factor_decay=case.factor_decay, hook_enabled=False)
+               factor_decay=case.factor_decay, hook_enabled=False, **case.extra)
     assert pre.modules == mods
+    mpd = not case.variant.endswith('_dp')
+    if pre.module_ranks is None:
+        pre.schedule_module_ranks()
     out = {}
     for s in range(case.steps):
         if case.lr_schedule is not None:
@@ -76,9 +79,9 @@ def _run_case(case, rank, world_size, dtype, port):
             li = synth_layer_inputs(spec, case.batch, hw_of.get(mod), case.seq, gen, dtype)
             if pre.steps % pre.param_groups[0]['fac_update_freq'] == 0:
                 ra, rg = pre.module_ranks[mod]
-                if rank == ra:
+                if mpd or rank == ra:
                     pre.m_a[mod] = li.a
-                if rank == rg:
+                if mpd or rank == rg:
                     pre.m_g[mod] = li.g
             w, b = synth_grads(spec, ggen, dtype)
             mod.weight.grad = w
@@ -90,15 +93,15 @@ def _run_case(case, rank, world_size, dtype, port):
             if mod.bias is not None:
                 out[f's{s}_l{l}_bgrad'] = digest(mod.bias.grad)
             ra, _ = pre.module_ranks[mod]
-            if rank == ra:
+            if mpd or rank == ra:
                 out[f's{s}_l{l}_A'] = digest(pre.m_A[mod])
                 out[f's{s}_l{l}_G'] = digest(pre.m_G[mod])
-                if case.variant == 'eigen_dp':
-                    out[f"s{s}_l{l}_dA"] = pre.m_dA[mod].numpy().copy()
-                    out[f"s{s}_l{l}_dG"] = pre.m_dG[mod].numpy().copy()
-                else:
-                    out[f's{s}_l{l}_invA'] = digest(pre.m_inv_A[mod])
-                    out[f's{s}_l{l}_invG'] = digest(pre.m_inv_G[mod])
+            if case.variant.startswith('eigen') and (mpd or rank == ra):
+                out[f"s{s}_l{l}_dA"] = pre.m_dA[mod].numpy().copy()
+                out[f"s{s}_l{l}_dG"] = pre.m_dG[mod].numpy().copy()
+            if case.variant.startswith('inverse') and (rank == ra or case.extra.get('communicate_inverse_or_not')):
+                out[f's{s}_l{l}_invA'] = digest(pre.m_inv_A[mod])
+                out[f's{s}_l{l}_invG'] = digest(pre.m_inv_G[mod])
             out[f's{s}_l{l}_precon'] = digest(pre.m_precon_grad[mod])
     return out
 

@@ -7,7 +7,7 @@ import os
 import numpy as np
 import torch
 
-from oracle.kfac_oracle import (OracleDPKFAC, specs_from_model, synth_grads,
+from oracle.kfac_oracle import (OracleDPKFAC, OracleMPDKFAC, specs_from_model, synth_grads,
                                 synth_layer_inputs)
 from tests.golden.cases import CASES_BY_NAME, digest, layer_input_hw
 
@@ -46,10 +46,13 @@ def run_oracle_case(case, dtype=torch.float32):
     """Returns a dict with the same keys as the fixture (minus the tag prefix),
     one copy per simulated rank."""
     model, specs, mods, hw_of = build_case(case)
-    orc = OracleDPKFAC(specs, variant=case.variant, lr=case.lr, damping=case.damping,
-                       fac_update_freq=case.fac_update_freq,
-                       kfac_update_freq=case.kfac_update_freq, kl_clip=case.kl_clip,
-                       factor_decay=case.factor_decay, world_size=case.world_size)
+    mpd = not case.variant.endswith('_dp')
+    cls = OracleMPDKFAC if mpd else OracleDPKFAC
+    orc = cls(specs, variant=case.variant, lr=case.lr, damping=case.damping,
+              fac_update_freq=case.fac_update_freq,
+              kfac_update_freq=case.kfac_update_freq, kl_clip=case.kl_clip,
+              factor_decay=case.factor_decay, world_size=case.world_size,
+              **{k: v for k, v in case.extra.items() if k == 'distribute_layer_factors'})
     out = {}
     for s in range(case.steps):
         lr = case.lr_schedule[s] if case.lr_schedule is not None else None
@@ -62,15 +65,16 @@ def run_oracle_case(case, dtype=torch.float32):
                 if ob[l] is not None:
                     out[pre + 'bgrad'] = digest(ob[l])
                 out[pre + 'precon'] = digest(orc.m_precon[l])
-                if orc.owners[l] == rank:
-                    out[pre + 'A'] = digest(orc.m_A[l])
-                    out[pre + 'G'] = digest(orc.m_G[l])
-                    if case.variant == 'eigen_dp':
-                        out[pre + 'dA'] = orc.m_dA[l].numpy().copy()
-                        out[pre + 'dG'] = orc.m_dG[l].numpy().copy()
-                    else:
-                        out[pre + 'invA'] = digest(orc.m_inv_A[l])
-                        out[pre + 'invG'] = digest(orc.m_inv_G[l])
+                owner = orc.owners[l] == rank
+                if mpd or owner:
+                    out[pre + 'A'] = digest(orc.m_A[rank][l] if mpd else orc.m_A[l])
+                    out[pre + 'G'] = digest(orc.m_G[rank][l] if mpd else orc.m_G[l])
+                if case.variant.startswith('eigen') and (mpd or owner):
+                    out[pre + 'dA'] = orc.m_dA[l].numpy().copy()
+                    out[pre + 'dG'] = orc.m_dG[l].numpy().copy()
+                if case.variant.startswith('inverse') and (owner or case.extra.get('communicate_inverse_or_not')):
+                    out[pre + 'invA'] = digest(orc.m_inv_A[l])
+                    out[pre + 'invG'] = digest(orc.m_inv_G[l])
     return out
 
 
@@ -115,8 +119,11 @@ def run_package_case(case, device, rank=0, engine=None, partition='round_robin')
     pre = KFAC(model, lr=case.lr, damping=case.damping, fac_update_freq=case.fac_update_freq,
                kfac_update_freq=case.kfac_update_freq, kl_clip=case.kl_clip,
                factor_decay=case.factor_decay, hook_enabled=False, engine=engine,
-               partition=partition)
+               partition=partition, **case.extra)
     assert pre.modules == mods
+    mpd = not case.variant.endswith('_dp')
+    if pre.module_ranks is None:
+        pre.schedule_module_ranks()
     out = {}
     for s in range(case.steps):
         if case.lr_schedule is not None:
@@ -125,9 +132,9 @@ def run_package_case(case, device, rank=0, engine=None, partition='round_robin')
         for l, mod in enumerate(mods):
             if pre.steps % pre.param_groups[0]['fac_update_freq'] == 0:
                 ra, rg = pre.module_ranks[mod]
-                if rank == ra:
+                if mpd or rank == ra:
                     pre.m_a[mod] = per_rank[rank][l].a.to(device)
-                if rank == rg:
+                if mpd or rank == rg:
                     pre.m_g[mod] = per_rank[rank][l].g.to(device)
             mod.weight.grad = wg[l].to(device)
             if bg[l] is not None:
@@ -139,15 +146,16 @@ def run_package_case(case, device, rank=0, engine=None, partition='round_robin')
             if mod.bias is not None:
                 out[p + 'bgrad'] = digest(mod.bias.grad)
             out[p + 'precon'] = digest(pre.m_precon_grad[mod])
-            if pre.module_ranks[mod][0] == rank:
+            owner = pre.module_ranks[mod][0] == rank
+            if mpd or owner:
                 out[p + 'A'] = digest(pre.m_A[mod])
                 out[p + 'G'] = digest(pre.m_G[mod])
-                if case.variant == 'eigen_dp':
-                    out[p + 'dA'] = pre.m_dA[mod].cpu().numpy().copy()
-                    out[p + 'dG'] = pre.m_dG[mod].cpu().numpy().copy()
-                else:
-                    out[p + 'invA'] = digest(pre.m_inv_A[mod])
-                    out[p + 'invG'] = digest(pre.m_inv_G[mod])
+            if case.variant.startswith('eigen') and (mpd or owner):
+                out[p + 'dA'] = pre.m_dA[mod].cpu().numpy().copy()
+                out[p + 'dG'] = pre.m_dG[mod].cpu().numpy().copy()
+            if case.variant.startswith('inverse') and (owner or case.extra.get('communicate_inverse_or_not')):
+                out[p + 'invA'] = digest(pre.m_inv_A[mod])
+                out[p + 'invG'] = digest(pre.m_inv_G[mod])
     return out, pre
 
 
