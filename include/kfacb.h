@@ -73,6 +73,8 @@ int32_t kfacb_layer_dA(const kfacb_layer_t* l);
 int32_t kfacb_layer_dG(const kfacb_layer_t* l);
 
 int         kfacb_version(void);
+/* sha256 of the sources + flags this library was built from (kfac_pytorch_b200/build.py) */
+const char* kfacb_build_fingerprint(void);
 /* number of CUDA kernels this library has launched in this process (monotonic; for benchmarking) */
 uint64_t    kfacb_launch_count(void);
 const char* kfacb_last_error(void);

@@ -46,12 +46,21 @@ def _fingerprint() -> str:
     return h.hexdigest()
 
 
+def built_fingerprint() -> str:
+    """Fingerprint compiled INTO the library (kfacb_build_fingerprint): travels with the .so wherever it goes."""
+    if not os.path.exists(LIB):
+        return ''
+    try:
+        import ctypes
+        lib = ctypes.CDLL(LIB)
+        lib.kfacb_build_fingerprint.restype = ctypes.c_char_p
+        return lib.kfacb_build_fingerprint().decode()
+    except Exception:
+        return ''
+
+
 def needs_build() -> bool:
-    stamp = os.path.join(LIBDIR, 'libkfacb.stamp')
-    if not (os.path.exists(LIB) and os.path.exists(stamp)):
-        return True
-    with open(stamp) as fh:
-        return fh.read().strip() != _fingerprint()
+    return built_fingerprint() != _fingerprint()
 
 
 def build(force: bool = False, verbose: bool = True) -> str:
@@ -61,9 +70,11 @@ def build(force: bool = False, verbose: bool = True) -> str:
     os.makedirs(OBJDIR, exist_ok=True)
     os.makedirs(LIBDIR, exist_ok=True)
 
+    fp = _fingerprint()
+
     def compile_one(src):
         obj = os.path.join(OBJDIR, src[:-3] + '.o')
-        cmd = [nvcc] + NVCC_FLAGS + ['-c', os.path.join(CSRC, src), '-o', obj]
+        cmd = [nvcc] + NVCC_FLAGS + ['-DKFACB_SRC_FINGERPRINT="%s"' % fp, '-c', os.path.join(CSRC, src), '-o', obj]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError('nvcc failed for %s:\n%s\n%s' % (src, r.stdout, r.stderr))
@@ -75,8 +86,6 @@ def build(force: bool = False, verbose: bool = True) -> str:
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError('link failed:\n%s\n%s' % (r.stdout, r.stderr))
-    with open(os.path.join(LIBDIR, 'libkfacb.stamp'), 'w') as fh:
-        fh.write(_fingerprint())
     if verbose:
         print('built', LIB)
     return LIB

@@ -38,6 +38,11 @@ int sm_count() {
 
 }  // namespace kfacb
 
+#ifndef KFACB_SRC_FINGERPRINT
+#define KFACB_SRC_FINGERPRINT "unknown"
+#endif
+extern "C" const char* kfacb_build_fingerprint(void) { return KFACB_SRC_FINGERPRINT; }
+
 extern "C" int kfacb_version(void) { return 100; }   /* 0.1.0 */
 
 extern "C" uint64_t kfacb_launch_count(void) { return __atomic_load_n(&kfacb::g_launches, __ATOMIC_RELAXED); }

@@ -35,7 +35,7 @@ class LayerDesc(C.Structure):
 
 
 EXPORTS = [
-    'kfacb_version', 'kfacb_launch_count', 'kfacb_last_error', 'kfacb_device_info', 'kfacb_layer_dA', 'kfacb_layer_dG',
+    'kfacb_version', 'kfacb_build_fingerprint', 'kfacb_launch_count', 'kfacb_last_error', 'kfacb_device_info', 'kfacb_layer_dA', 'kfacb_layer_dG',
     'kfacb_factor_workspace_bytes', 'kfacb_factor_update',
     'kfacb_eigh_workspace_bytes', 'kfacb_eigh_batched', 'kfacb_eigh_last_profile',
     'kfacb_spd_inverse_workspace_bytes', 'kfacb_pi_damped_inverse',
@@ -65,6 +65,7 @@ def load_library(path: Optional[str] = None):
     I32P = C.POINTER(C.c_int32)
     LP = C.POINTER(LayerDesc)
     lib.kfacb_version.restype = C.c_int
+    lib.kfacb_build_fingerprint.restype = C.c_char_p
     lib.kfacb_launch_count.restype = C.c_uint64
     lib.kfacb_last_error.restype = C.c_char_p
     lib.kfacb_device_info.argtypes = [I32P, I32P, I32P]
