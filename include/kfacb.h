@@ -114,7 +114,7 @@ int    kfacb_factor_update(const kfacb_layer_t* layers, int32_t count,
  * For each i: M[i] (n[i] x n[i], symmetric, read only) = Q diag(d) Q^T with d
  * ascending, eigenvectors in the COLUMNS of Q[i] (row-major n x n), then
  * d <- d * (d > eps_floor).  Jacobi based (one CTA per matrix in shared memory
- * for n <= 128, blocked one-sided Jacobi above); eigenvectors are defined up
+ * for n <= 128, implicit two-sided block Jacobi above); eigenvectors are defined up
  * to sign / rotation inside degenerate clusters.
  * sweeps_out (device int32[count], may be NULL) receives the number of sweeps.
  * ------------------------------------------------------------------------- */

@@ -28,10 +28,10 @@ namespace kfacb {
 
 constexpr int BJ_B = 64;              // rows per block
 constexpr int BJ_M = 2 * BJ_B;        // rows per pair = size of the inner eigenproblem (= TILE)
-constexpr int BJ_KCHUNK = 512;        // split-K chunk of the projected-block GEMM
+constexpr int BJ_KCHUNK = 512;        // largest split-K chunk of the projected-block GEMM (the host picks 256/384/512)
 static_assert(BJ_M == TILE, "a pair is one 128-row GEMM tile");
 constexpr int BJ_MAX_SWEEPS = 16;
-constexpr int BJ_INNER_SWEEPS = 1;    // cap of Jacobi sweeps on the 64x64 Gram per visit
+    // cap of Jacobi sweeps on the 64x64 Gram per visit
 constexpr int DIRECT_MAX_N = 128;
 
 struct BjMat {
@@ -45,7 +45,8 @@ struct BjMat {
     int n, n_pad, p;      // p = even number of blocks (incl. a dummy when odd)
     int nblk;             // real number of blocks
     int pair_begin;       // first global pair index of this matrix
-    int ksplit;           // Gram split-K factor
+    int ksplit;           // projected-block split-K factor = ceil(n_pad / kchunk)
+    int kchunk;           // k-chunk of one projected-block CTA
     float tol_conv;       // sweep-time off-norm / ||A||_F below which the matrix is converged
 };
 
@@ -324,7 +325,7 @@ bj_h_tc_kernel(const BjMat* mats, const int* pair_mat, const BjState* state, int
     tcg::Ctx c;
     tcg::setup(c, dsm_raw, &mbar, &tmem_slot);
     const long ld = 2L * mt.n_pad;
-    const int kbeg = zchunk * BJ_KCHUNK, kend = min(mt.n_pad, kbeg + BJ_KCHUNK);
+    const int kbeg = zchunk * mt.kchunk, kend = min(mt.n_pad, kbeg + mt.kchunk);
     LdPairRows lv{mt.X + mt.n_pad, ld, bi * BJ_B, bj * BJ_B, kend};      // V rows
     LdPairRows lw{mt.X, ld, bi * BJ_B, bj * BJ_B, kend};                 // W rows
     tcg::mainloop<false>(lv, lw, 0, 0, kbeg, kend, false, c);     // 64 K-steps per chunk; H only steers the rotations
@@ -346,7 +347,10 @@ bj_h_tc_kernel(const BjMat* mats, const int* pair_mat, const BjState* state, int
 //     tcgen05.commit -> mbarrier;
 //   * warps 8-11 (epilogue): wait for the tile's accumulator (2 x 128 TMEM columns, double buffered),
 //     tcgen05.ld it and store the rows back in place (lanes = consecutive columns: coalesced).
-// grid (ceil(col_tiles / tiles_per_cta), total_pairs)
+// (A 13th warp dedicated to the UMMA issue was measured slower: 416 threads cap the kernel at 128 registers
+// and the producers spill.)
+// grid (ceil(col_tiles / tiles_per_cta), total_pairs); tiles_per_cta is chosen per group by the host so that
+// the CTA count fills whole waves of the 148 SMs (1 CTA / SM).
 constexpr int UPD_PRODUCERS = 256;                       // 8 producer warps
 constexpr int UPD_THREADS = UPD_PRODUCERS + 128;         // + 4 epilogue warps
 constexpr int UPD_LBO = (TILE / 8) * 128;                 // 2048: stride between k-quads
@@ -401,6 +405,30 @@ bj_update_tc_kernel(const BjMat* mats, const int* pair_mat, const BjState* state
     tc::tc_fence_after();
     const uint32_t tmem = tmem_slot;
     const int row_a = bi * BJ_B, row_b = bj * BJ_B;
+    // the 12 UMMAs of k-slab q (3xTF32: hi*hi + lo*hi + hi*lo), by ONE thread
+    auto issue_slab = [&](int q) {
+        const int b = q & 1;
+        const int t = q >> 2, sl = q & 3, tb = t & 1, ut = t >> 1;
+        if (sl == 0 && ut > 0) tc::mbar_wait(&bar_empty[tb], (uint32_t)((ut - 1) & 1));   // accumulator drained
+        tc::tc_fence_after();
+        constexpr uint32_t idesc = tc::idesc_tf32(128, 128, 0, 0);
+        const uint32_t ah = tc::smem_u32(a_buf) + (2 * b) * UPD_A_PART, al = ah + UPD_A_PART;
+        const uint32_t bh = tc::smem_u32(u_hi) + 8 * sl * UPD_LBO, bl = tc::smem_u32(u_lo) + 8 * sl * UPD_LBO;
+        const uint32_t d = tmem + 128 * tb;
+#pragma unroll
+        for (int pass = 0; pass < 3; ++pass) {
+            const uint32_t ab = pass == 1 ? al : ah;
+            const uint32_t bb = pass == 2 ? bl : bh;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const uint64_t ad = tc::smem_desc(ab + 2 * j * UPD_LBO, UPD_LBO, 128);
+                const uint64_t bd = tc::smem_desc(bb + 2 * j * UPD_LBO, UPD_LBO, 128);
+                tc::umma_tf32(d, ad, bd, idesc, !(sl == 0 && pass == 0 && j == 0));
+            }
+        }
+        tc::umma_commit(&bar_smem[b]);
+        if (sl == 3) tc::umma_commit(&bar_full[tb]);
+    };
 
     if (warp < UPD_PRODUCERS / 32) {
         // ===================== producers: load / split / stage / issue =====================
@@ -423,7 +451,7 @@ bj_update_tc_kernel(const BjMat* mats, const int* pair_mat, const BjState* state
                 for (int kk = 0; kk < 16; ++kk) dst[kk] = 0.f;
             }
         };
-        auto stage_and_issue = [&](int q, float (&src)[16]) {
+        auto stage_slab = [&](int q, float (&src)[16]) {
             const int b = q & 1, u = q >> 1;
             if (u > 0) tc::mbar_wait(&bar_smem[b], (uint32_t)((u - 1) & 1));        // buffer b free again
             unsigned char* hi_p = a_buf + (2 * b) * UPD_A_PART;
@@ -439,35 +467,14 @@ bj_update_tc_kernel(const BjMat* mats, const int* pair_mat, const BjState* state
             load_slab(q + 4, src);                           // refill the registers: in flight for four slabs
             tc::fence_async_smem();
             tc::named_bar_sync(1, UPD_PRODUCERS);
-            if (tid == 0) {
-                const int t = q >> 2, sl = q & 3, tb = t & 1, ut = t >> 1;
-                if (sl == 0 && ut > 0) tc::mbar_wait(&bar_empty[tb], (uint32_t)((ut - 1) & 1));   // accumulator drained
-                tc::tc_fence_after();
-                constexpr uint32_t idesc = tc::idesc_tf32(128, 128, 0, 0);
-                const uint32_t ah = tc::smem_u32(hi_p), al = tc::smem_u32(lo_p);
-                const uint32_t bh = tc::smem_u32(u_hi) + 8 * sl * UPD_LBO, bl = tc::smem_u32(u_lo) + 8 * sl * UPD_LBO;
-                const uint32_t d = tmem + 128 * tb;
-#pragma unroll
-                for (int pass = 0; pass < 3; ++pass) {
-                    const uint32_t ab = pass == 1 ? al : ah;
-                    const uint32_t bb = pass == 2 ? bl : bh;
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const uint64_t ad = tc::smem_desc(ab + 2 * j * UPD_LBO, UPD_LBO, 128);
-                        const uint64_t bd = tc::smem_desc(bb + 2 * j * UPD_LBO, UPD_LBO, 128);
-                        tc::umma_tf32(d, ad, bd, idesc, !(sl == 0 && pass == 0 && j == 0));
-                    }
-                }
-                tc::umma_commit(&bar_smem[b]);
-                if (sl == 3) tc::umma_commit(&bar_full[tb]);
-            }
+            if (tid == 0) issue_slab(q);
         };
         load_slab(0, x[0]); load_slab(1, x[1]); load_slab(2, x[2]); load_slab(3, x[3]);
         for (int q = 0; q < nslab; q += 4) {                 // nslab is a multiple of 4
-            stage_and_issue(q, x[0]);
-            stage_and_issue(q + 1, x[1]);
-            stage_and_issue(q + 2, x[2]);
-            stage_and_issue(q + 3, x[3]);
+            stage_slab(q, x[0]);
+            stage_slab(q + 1, x[1]);
+            stage_slab(q + 2, x[2]);
+            stage_slab(q + 3, x[3]);
         }
     } else {
         // ===================== epilogue: TMEM -> rows of X, in place =====================
@@ -502,205 +509,289 @@ bj_update_tc_kernel(const BjMat* mats, const int* pair_mat, const BjState* state
 }
 
 // (2) inner eigenproblem: fixed-order sum of the H partials, symmetrise, one cyclic two-sided Jacobi
-// sweep of the 128x128 block in shared memory, emit the accumulated rotations U.  grid total_pairs.
+// sweep of the 128x128 block in shared memory, emit the accumulated rotations U.
 // Element pairs inside one 64-row block meet in EVERY round of the outer sweep, pairs across the two
 // blocks meet only here: bipartite 64-round tournament {(i, 64 + (i + r) % 64)} normally, the full
-// 127-round tournament in the first round(s) of each outer sweep.  Rotation application is fully
-// unrolled and branch-free (skipped pairs carry c = 1, s = 0), one float4 {c, s, p, q} per pair.
-constexpr int SOLVE_THREADS = 1024;
+// 127-round tournament in the first round(s) of each outer sweep.
+// In bipartite rounds S' = J^T S J decomposes into independent 2x2 blocks (pair a x pair b): one thread loads the
+// 4 entries, applies the right (pair b) and left (pair a) rotation in registers and stores them -- each element of
+// S is read and written once per round.  Rotation application is branch-free (skipped pairs carry c = 1, s = 0).
+//
+// Two layouts of the same arithmetic (bit-identical results), chosen by the host per group:
+//   SPLIT = false  one CTA of 1024 threads per pair holds S and U (132 KB): best THROUGHPUT when there are
+//                  more pairs than SMs (the sweep is bound by shared-memory bandwidth either way);
+//   SPLIT = true   a CLUSTER OF TWO CTAs (512 threads, 66 KB each) per pair: best LATENCY when the pairs cannot
+//                  fill the SMs (one large factor per GPU).
+//     * CTA 0 ("S") owns the projected block S, computes the rotations of every round and applies them to S;
+//       each round's 64 rotations {c, s, p, q} are published to a global log + a release flag;
+//     * CTA 1 ("U") owns the accumulator U, follows the log (acquire on the flag) and applies the same
+//       rotations to U.  U never feeds back into S, so the two run concurrently, U lagging by < 1 round.
+//     The cluster guarantees co-scheduling (S never waits on U, so the spin in U cannot deadlock).
 constexpr int SOLVE_P = BJ_M + 1;
-constexpr int SOLVE_SMEM = 2 * BJ_M * SOLVE_P * (int)sizeof(float);
-__global__ void __launch_bounds__(SOLVE_THREADS)
+constexpr int SOLVE_MAX_ROUNDS = BJ_M - 1;                   // 127 (full tournament)
+constexpr int SOLVE_LOG_STRIDE = SOLVE_MAX_ROUNDS * (BJ_M / 2);   // float4 entries per pair
+template <bool SPLIT>
+struct SolveCfg {
+    static constexpr int THREADS = SPLIT ? 512 : 1024;
+    static constexpr int SMEM = (SPLIT ? 1 : 2) * BJ_M * SOLVE_P * (int)sizeof(float);
+};
+
+__device__ __forceinline__ int ld_acquire(const int* p) {
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release(int* p, int v) {
+    asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// X <- X J for the rotations rb[0..64) of one round; this thread: row `row`, pairs grp, grp + GROUPS, ...
+// (the pairs of a round are disjoint: loads of a chunk first, then its stores)
+template <int GROUPS, int CH>
+__device__ __forceinline__ void solve_rotate_columns(float* X, const float4* rb, int row, int grp) {
+    constexpr int P = SOLVE_P, PPT = (BJ_M / 2) / GROUPS;
+#pragma unroll
+    for (int u0 = 0; u0 < PPT; u0 += CH) {
+        float4 rp[CH];
+        float xp[CH], xq[CH];
+#pragma unroll
+        for (int u = 0; u < CH; ++u) {
+            rp[u] = rb[grp + GROUPS * (u0 + u)];
+            xp[u] = X[row * P + __float_as_int(rp[u].z)];
+            xq[u] = X[row * P + __float_as_int(rp[u].w)];
+        }
+#pragma unroll
+        for (int u = 0; u < CH; ++u) {
+            X[row * P + __float_as_int(rp[u].z)] = rp[u].x * xp[u] - rp[u].y * xq[u];
+            X[row * P + __float_as_int(rp[u].w)] = rp[u].y * xp[u] + rp[u].x * xq[u];
+        }
+    }
+}
+
+template <bool SPLIT>
+__global__ void __launch_bounds__(SolveCfg<SPLIT>::THREADS, 1)
 bj_solve_kernel(const BjMat* mats, const int* pair_mat, BjState* state, int round,
                 const float* __restrict__ partial, const long* partial_off,
-                float* __restrict__ ubuf, int inner_sweeps, int full_inner) {
+                float* __restrict__ ubuf, float4* __restrict__ rotlog, int* __restrict__ rotflag,
+                int epoch, int full_inner) {
     constexpr int M = BJ_M, P = SOLVE_P, HALF = BJ_M / 2, MM1 = BJ_M - 1;
-    constexpr int GROUPS = SOLVE_THREADS / M;                // 8
-    constexpr int PPT = HALF / GROUPS;                       // pairs per thread per phase (8)
+    constexpr int THREADS = SolveCfg<SPLIT>::THREADS;
+    constexpr int GROUPS = THREADS / M;                      // 4 | 8 row groups
+    constexpr int RCH = SPLIT ? 16 : 8;                      // rotations per load/store batch (the split layout has registers to spare)
     extern __shared__ float sm_f[];
-    float* S = sm_f;
-    float* U = sm_f + M * P;
-    __shared__ float4 rot[HALF];
-    __shared__ float red[SOLVE_THREADS / 32];
-    const int mi = pair_mat[blockIdx.x];
+    float* S = sm_f;                                         // SPLIT: the matrix of this CTA's role (S or U)
+    float* U = SPLIT ? sm_f : sm_f + M * P;
+    __shared__ float4 rot[2][HALF];                          // S side uses rot[0]; the U follower double-buffers
+    __shared__ float red[THREADS / 32];
+    __shared__ int s_avail[2];
+    const int pair_idx = SPLIT ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+    const int role = SPLIT ? (int)(blockIdx.x & 1) : 0;      // 0 = S (+ U when not split), 1 = U follower
+    const int mi = pair_mat[pair_idx];
     const BjMat mt = mats[mi];
-    if (state[mi].converged) return;
+    if (state[mi].converged) return;                         // (both CTAs of a cluster take the same exit)
     int bi, bj;
-    if (!bj_pair_blocks(mt, blockIdx.x - mt.pair_begin, round, bi, bj)) return;
+    if (!bj_pair_blocks(mt, pair_idx - mt.pair_begin, round, bi, bj)) return;
     const int tid = threadIdx.x;
+    // (with an odd block count one block idles per round: two leading full rounds cover every block)
+    const bool full = full_inner || (round % (mt.p - 1)) < ((mt.nblk & 1) ? 2 : 1);
+    const int nrounds = full ? MM1 : BJ_B;
+    float4* log = rotlog + (long)pair_idx * SOLVE_LOG_STRIDE;
+    int* flag = rotflag + pair_idx;
+    const int flag_base = epoch << 8;                        // rounds < 256: (epoch, round) packs into one int
+    const int row = tid & (M - 1), grp = tid / M;
+    float* dst = ubuf + (long)pair_idx * (M * M);
+
+    if (SPLIT && role == 1) {
+        // ============================ U: follow the rotation log ============================
+        for (int e = tid; e < M * M; e += THREADS) {
+            const int i = e / M, j = e - i * M;
+            U[i * P + j] = (i == j) ? 1.f : 0.f;
+        }
+        // `avail` = rounds known to be published.  The flag is polled only when U has caught up with S; while
+        // it lags, the next round's rotations are prefetched into shared memory (cp.async, L2 only) during the
+        // current round, so the L2 latency of flag + log is off the critical path.
+        int avail = 0;
+        bool pref = false;
+        for (int r = 0; r < nrounds; ++r) {
+            float4* rb = rot[r & 1];
+            if (pref) {
+                if (tid < HALF) asm volatile("cp.async.wait_all;" ::: "memory");
+                __syncthreads();
+            } else {                                         // (r >= avail here)
+                if (tid == 0) {
+                    int v;
+                    while ((v = ld_acquire(flag)) < flag_base + r + 1) { }
+                    s_avail[r & 1] = v - flag_base;
+                }
+                __syncthreads();                             // round r is published; round r-1 of U is complete
+                avail = s_avail[r & 1];
+                if (tid < HALF) rb[tid] = __ldcg(log + r * HALF + tid);
+                __syncthreads();
+            }
+            pref = r + 1 < avail;
+            if (pref && tid < HALF) {
+                const unsigned d = (unsigned)__cvta_generic_to_shared(&rot[(r + 1) & 1][tid]);
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(log + (r + 1) * HALF + tid)
+                             : "memory");
+                asm volatile("cp.async.commit_group;" ::: "memory");
+            }
+            solve_rotate_columns<GROUPS, RCH>(U, rb, row, grp);
+        }
+        __syncthreads();
+        for (int e = tid; e < M * M; e += THREADS) {
+            const int i = e / M, j = e - i * M;
+            dst[e] = U[i * P + j];
+        }
+        return;
+    }
+
+    // ============================ S: rotations (+ U when not split) ============================
     const float* src = partial + partial_off[mi] +
-                       (long)(blockIdx.x - mt.pair_begin) * mt.ksplit * (M * M);
-    // sum the split-K partials: float4 loads, 3 independent accumulators in flight (fixed order => deterministic)
+                       (long)(pair_idx - mt.pair_begin) * mt.ksplit * (M * M);
+    // sum the split-K partials in chunk order (fixed => deterministic): float4 loads, 4 independent elements in flight
     {
         const float4* src4 = reinterpret_cast<const float4*>(src);
+        constexpr int NH = (M * M / 4) / THREADS;            // float4 elements per thread: 4 | 8
 #pragma unroll
-        for (int h = 0; h < (M * M / 4) / SOLVE_THREADS; ++h) {
-            const int e4 = tid + h * SOLVE_THREADS;
-            float4 acc[3];
+        for (int h0 = 0; h0 < NH; h0 += 4) {
+            float4 acc[4];
 #pragma unroll
-            for (int u = 0; u < 3; ++u) acc[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-            int z = 0;
-            for (; z + 3 <= mt.ksplit; z += 3) {
+            for (int u = 0; u < 4; ++u) acc[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int z = 0; z < mt.ksplit; ++z) {
 #pragma unroll
-                for (int u = 0; u < 3; ++u) {
-                    const float4 t = __ldg(src4 + (long)(z + u) * (M * M / 4) + e4);
+                for (int u = 0; u < 4; ++u) {
+                    const float4 t = __ldg(src4 + (long)z * (M * M / 4) + tid + (h0 + u) * THREADS);
                     acc[u].x += t.x; acc[u].y += t.y; acc[u].z += t.z; acc[u].w += t.w;
                 }
             }
-            for (; z < mt.ksplit; ++z) {
-                const float4 t = __ldg(src4 + (long)z * (M * M / 4) + e4);
-                acc[0].x += t.x; acc[0].y += t.y; acc[0].z += t.z; acc[0].w += t.w;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int e4 = tid + (h0 + u) * THREADS;
+                const int i = (e4 * 4) / M, j = (e4 * 4) - i * M;
+                S[i * P + j] = acc[u].x; S[i * P + j + 1] = acc[u].y;
+                S[i * P + j + 2] = acc[u].z; S[i * P + j + 3] = acc[u].w;
             }
-            const int i = (e4 * 4) / M, j = (e4 * 4) - i * M;
-            U[i * P + j] = (acc[0].x + acc[1].x) + acc[2].x;          // U = raw H for now
-            U[i * P + j + 1] = (acc[0].y + acc[1].y) + acc[2].y;
-            U[i * P + j + 2] = (acc[0].z + acc[1].z) + acc[2].z;
-            U[i * P + j + 3] = (acc[0].w + acc[1].w) + acc[2].w;
         }
     }
     __syncthreads();
+    // H is symmetric only up to rounding: S = (H + H^T)/2, in place (each unordered pair by one thread)
     float off2 = 0.f;
-    for (int e = tid; e < M * M; e += SOLVE_THREADS) {      // H is symmetric only up to rounding: S = (H + H^T)/2
+    for (int e = tid; e < M * M; e += THREADS) {
         const int i = e / M, j = e - i * M;
-        const float v = 0.5f * (U[i * P + j] + U[j * P + i]);
-        S[i * P + j] = v;
-        if (i < BJ_B && j >= BJ_B) off2 = fmaf(v, v, off2);     // cross block (counted once)
-    }
-    __syncthreads();
-    for (int e = tid; e < M * M; e += SOLVE_THREADS) {
-        const int i = e / M, j = e - i * M;
-        U[i * P + j] = (i == j) ? 1.f : 0.f;
+        if (i < j) {
+            const float v = 0.5f * (S[i * P + j] + S[j * P + i]);
+            S[i * P + j] = v; S[j * P + i] = v;
+            if (i < BJ_B && j >= BJ_B) off2 = fmaf(v, v, off2);     // cross block (counted once)
+        }
+        if (!SPLIT) U[i * P + j] = (i == j) ? 1.f : 0.f;
     }
     off2 = warp_sum(off2);
     if ((tid & 31) == 0) red[tid >> 5] = off2;
     __syncthreads();
     if (tid == 0) {
         float t = 0.f;
-        for (int i = 0; i < SOLVE_THREADS / 32; ++i) t += red[i];
+        for (int i = 0; i < THREADS / 32; ++i) t += red[i];
         if (t > 0.f) atomicAdd(&state[mi].off2, 2.f * t);
     }
     const float abs_thr = 5e-8f * __int_as_float(state[mi].scale_bits);
-    const int row = tid & (M - 1), grp = tid / M;            // grp in [0, 8)
-    // (with an odd block count one block idles per round: two leading full rounds cover every block)
-    const bool full = full_inner || (round % (mt.p - 1)) < ((mt.nblk & 1) ? 2 : 1);
-    const int nrounds = full ? MM1 : BJ_B;
-    for (int sw = 0; sw < inner_sweeps; ++sw) {
-        int any = 0;
-        for (int r = 0; r < nrounds; ++r) {
-            if (tid < HALF) {
-                int p, q;
-                if (full) {
-                    if (tid == 0) { p = MM1; q = r; }
-                    else { p = r + tid; if (p >= MM1) p -= MM1; q = r - tid; if (q < 0) q += MM1; }
-                    if (p > q) { const int t = p; p = q; q = t; }
-                } else {
-                    p = tid; q = BJ_B + ((tid + r) & (BJ_B - 1));
-                }
-                const float app = S[p * P + p], aqq = S[q * P + q], apq = S[p * P + q];
-                float c = 1.f, sn = 0.f;
-                const float mag = fabsf(apq);
-                if (mag > 1.0e-7f * sqrtf(fabsf(app) * fabsf(aqq)) && mag > abs_thr) {
-                    // angle from fast divide / sqrt (an angle error only leaves a residual a_pq);
-                    // (c, s) is then re-normalised so that c^2 + s^2 = 1 to fp32 rounding.
-                    const float tau = __fdividef(aqq - app, 2.f * apq);
-                    const float t = __fdividef(tau >= 0.f ? 1.f : -1.f, fabsf(tau) + __fsqrt_rn(fmaf(tau, tau, 1.f)));
-                    c = rsqrtf(fmaf(t, t, 1.f));
-                    sn = t * c;
-                    const float f = fmaf(-0.5f, fmaf(c, c, sn * sn), 1.5f);
-                    c *= f; sn *= f;
-                    any = 1;
-                }
-                rot[tid] = make_float4(c, sn, __int_as_float(p), __int_as_float(q));
+    for (int r = 0; r < nrounds; ++r) {
+        if (tid < HALF) {
+            int p, q;
+            if (full) {
+                if (tid == 0) { p = MM1; q = r; }
+                else { p = r + tid; if (p >= MM1) p -= MM1; q = r - tid; if (q < 0) q += MM1; }
+                if (p > q) { const int t = p; p = q; q = t; }
+            } else {
+                p = tid; q = BJ_B + ((tid + r) & (BJ_B - 1));
             }
-            __syncthreads();
-            if (!full) {
-                // Bipartite round: pair k = (k, 64 + (k + r) % 64).  S' = J^T S J decomposes into independent 2x2
-                // blocks indexed by (pair a, pair b): one thread loads the 4 entries, applies the right rotation
-                // (pair b) and the left rotation (pair a) in registers and stores them -- each element of S is
-                // read and written ONCE per round (the separate column/row passes touch it twice), and there
-                // is no barrier between the S and U updates.  Lanes walk b: conflict-free (pitch 129).
-                const int b = tid & (HALF - 1);
-                const float4 rb = rot[b];
-                const int qb = __float_as_int(rb.w);
+            const float app = S[p * P + p], aqq = S[q * P + q], apq = S[p * P + q];
+            float c = 1.f, sn = 0.f;
+            const float mag = fabsf(apq);
+            if (mag > 1.0e-7f * sqrtf(fabsf(app) * fabsf(aqq)) && mag > abs_thr) {
+                // angle from fast divide / sqrt (an angle error only leaves a residual a_pq);
+                // (c, s) is then re-normalised so that c^2 + s^2 = 1 to fp32 rounding.
+                const float tau = __fdividef(aqq - app, 2.f * apq);
+                const float t = __fdividef(tau >= 0.f ? 1.f : -1.f, fabsf(tau) + __fsqrt_rn(fmaf(tau, tau, 1.f)));
+                c = rsqrtf(fmaf(t, t, 1.f));
+                sn = t * c;
+                const float f = fmaf(-0.5f, fmaf(c, c, sn * sn), 1.5f);
+                c *= f; sn *= f;
+            }
+            const float4 rv = make_float4(c, sn, __int_as_float(p), __int_as_float(q));
+            rot[0][tid] = rv;
+            if (SPLIT) log[r * HALF + tid] = rv;             // for the U CTA
+        }
+        __syncthreads();
+        if (SPLIT && tid == 0) st_release(flag, flag_base + r + 1);   // publishes the log entries written before the barrier
+        if (!full) {
+            // 2x2 blocks (pair a, pair b); lanes walk b: conflict-free (pitch 129)
+            const int b = tid & (HALF - 1);
+            const float4 rb = rot[0][b];
+            const int qb = __float_as_int(rb.w);
+            constexpr int AG = THREADS / HALF;                          // 8 | 16 groups of pair a
+            constexpr int NIT = HALF / AG;                              // 8 | 4 2x2 blocks per thread ...
+            constexpr int CH = SPLIT ? 8 : 4;                           // ... in chunks: 16 | 32 loads in flight
 #pragma unroll
-                for (int i = 0; i < HALF / (SOLVE_THREADS / HALF); ++i) {
-                    const int a = (tid >> 6) + (SOLVE_THREADS / HALF) * i;
-                    const float4 ra = rot[a];
-                    const int qa = __float_as_int(ra.w);
-                    const float x11 = S[a * P + b], x12 = S[a * P + qb], x21 = S[qa * P + b], x22 = S[qa * P + qb];
-                    const float y11 = rb.x * x11 - rb.y * x12, y12 = rb.y * x11 + rb.x * x12;
-                    const float y21 = rb.x * x21 - rb.y * x22, y22 = rb.y * x21 + rb.x * x22;
-                    float z11 = ra.x * y11 - ra.y * y21, z21 = ra.y * y11 + ra.x * y21;
-                    float z12 = ra.x * y12 - ra.y * y22, z22 = ra.y * y12 + ra.x * y22;
-                    if (a == b && ra.y != 0.f) { z12 = 0.f; z21 = 0.f; }     // the annihilated element
+            for (int i0 = 0; i0 < NIT; i0 += CH) {
+                float4 ra[CH];
+                float x11[CH], x12[CH], x21[CH], x22[CH];
+#pragma unroll
+                for (int i = 0; i < CH; ++i) {
+                    const int a = (tid >> 6) + AG * (i0 + i);
+                    ra[i] = rot[0][a];
+                    const int qa = __float_as_int(ra[i].w);
+                    x11[i] = S[a * P + b]; x12[i] = S[a * P + qb]; x21[i] = S[qa * P + b]; x22[i] = S[qa * P + qb];
+                }
+#pragma unroll
+                for (int i = 0; i < CH; ++i) {
+                    const int a = (tid >> 6) + AG * (i0 + i);
+                    const int qa = __float_as_int(ra[i].w);
+                    const float y11 = rb.x * x11[i] - rb.y * x12[i], y12 = rb.y * x11[i] + rb.x * x12[i];
+                    const float y21 = rb.x * x21[i] - rb.y * x22[i], y22 = rb.y * x21[i] + rb.x * x22[i];
+                    float z11 = ra[i].x * y11 - ra[i].y * y21, z21 = ra[i].y * y11 + ra[i].x * y21;
+                    float z12 = ra[i].x * y12 - ra[i].y * y22, z22 = ra[i].y * y12 + ra[i].x * y22;
+                    if (a == b && ra[i].y != 0.f) { z12 = 0.f; z21 = 0.f; }     // the annihilated element
                     S[a * P + b] = z11; S[a * P + qb] = z12; S[qa * P + b] = z21; S[qa * P + qb] = z22;
                 }
-                // U <- U J: rows walk the lanes, 8 pairs per thread
-#pragma unroll
-                for (int u = 0; u < PPT; ++u) {
-                    const float4 rp = rot[grp + GROUPS * u];
-                    const int pp = __float_as_int(rp.z), qq = __float_as_int(rp.w);
-                    const float up = U[row * P + pp], uq = U[row * P + qq];
-                    U[row * P + pp] = rp.x * up - rp.y * uq;
-                    U[row * P + qq] = rp.y * up + rp.x * uq;
-                }
-                __syncthreads();
-                continue;
             }
-            // generic (full tournament) round: column pass, barrier, row pass
-            // column rotations: S <- S J, U <- U J   (this thread: row `row`, pairs grp, grp+8, ...)
-            {
-                float4 rp[PPT];
-                float sp[PPT], sq[PPT], up[PPT], uq[PPT];
-#pragma unroll
-                for (int u = 0; u < PPT; ++u) rp[u] = rot[grp + GROUPS * u];
-#pragma unroll
-                for (int u = 0; u < PPT; ++u) {
-                    const int p = __float_as_int(rp[u].z), q = __float_as_int(rp[u].w);
-                    sp[u] = S[row * P + p]; sq[u] = S[row * P + q];
-                    up[u] = U[row * P + p]; uq[u] = U[row * P + q];
-                }
-#pragma unroll
-                for (int u = 0; u < PPT; ++u) {
-                    const int p = __float_as_int(rp[u].z), q = __float_as_int(rp[u].w);
-                    const float c = rp[u].x, sn = rp[u].y;
-                    S[row * P + p] = c * sp[u] - sn * sq[u];
-                    S[row * P + q] = sn * sp[u] + c * sq[u];
-                    U[row * P + p] = c * up[u] - sn * uq[u];
-                    U[row * P + q] = sn * up[u] + c * uq[u];
-                }
-            }
+            if (!SPLIT) solve_rotate_columns<GROUPS, RCH>(U, rot[0], row, grp);     // U <- U J (no barrier needed before)
             __syncthreads();
-            // row rotations: S <- J^T S   (this thread: column `row`); the rotated pair element is set to 0
-            {
-                float4 rp[PPT];
-                float sp[PPT], sq[PPT];
-#pragma unroll
-                for (int u = 0; u < PPT; ++u) rp[u] = rot[grp + GROUPS * u];
-#pragma unroll
-                for (int u = 0; u < PPT; ++u) {
-                    const int p = __float_as_int(rp[u].z), q = __float_as_int(rp[u].w);
-                    sp[u] = S[p * P + row]; sq[u] = S[q * P + row];
-                }
-#pragma unroll
-                for (int u = 0; u < PPT; ++u) {
-                    const int p = __float_as_int(rp[u].z), q = __float_as_int(rp[u].w);
-                    const float c = rp[u].x, sn = rp[u].y;
-                    float np = c * sp[u] - sn * sq[u];
-                    float nq = sn * sp[u] + c * sq[u];
-                    if (sn != 0.f) { if (row == q) np = 0.f; if (row == p) nq = 0.f; }
-                    S[p * P + row] = np;
-                    S[q * P + row] = nq;
-                }
-            }
-            __syncthreads();
+            continue;
         }
-        if (!__syncthreads_or(any)) break;
+        // generic (full tournament) round: column pass (S and U), barrier, row pass
+        solve_rotate_columns<GROUPS, RCH>(S, rot[0], row, grp);
+        if (!SPLIT) solve_rotate_columns<GROUPS, RCH>(U, rot[0], row, grp);
+        __syncthreads();
+        {
+            constexpr int PPT = HALF / GROUPS, CH = 8;
+#pragma unroll
+            for (int u0 = 0; u0 < PPT; u0 += CH) {
+                float4 rp[CH];
+                float sp[CH], sq[CH];
+#pragma unroll
+                for (int u = 0; u < CH; ++u) {
+                    rp[u] = rot[0][grp + GROUPS * (u0 + u)];
+                    sp[u] = S[__float_as_int(rp[u].z) * P + row];
+                    sq[u] = S[__float_as_int(rp[u].w) * P + row];
+                }
+#pragma unroll
+                for (int u = 0; u < CH; ++u) {
+                    const int pp = __float_as_int(rp[u].z), qq = __float_as_int(rp[u].w);
+                    float np = rp[u].x * sp[u] - rp[u].y * sq[u];
+                    float nq = rp[u].y * sp[u] + rp[u].x * sq[u];
+                    if (rp[u].y != 0.f) { if (row == qq) np = 0.f; if (row == pp) nq = 0.f; }   // the rotated pair element
+                    S[pp * P + row] = np;
+                    S[qq * P + row] = nq;
+                }
+            }
+        }
+        __syncthreads();
     }
-    float* dst = ubuf + (long)blockIdx.x * (M * M);
-    for (int e = tid; e < M * M; e += SOLVE_THREADS) {
-        const int i = e / M, j = e - i * M;
-        dst[e] = U[i * P + j];
+    if (!SPLIT) {
+        for (int e = tid; e < M * M; e += THREADS) {
+            const int i = e / M, j = e - i * M;
+            dst[e] = U[i * P + j];
+        }
     }
 }
 
@@ -855,10 +946,13 @@ constexpr int MAX_GROUPS = 4;
 
 struct GroupPlan {
     int nb = 0, total_pairs = 0, max_ksplit = 1, max_rounds = 0, nmax = 0;
+    int kchunk = BJ_KCHUNK;       // k-chunk of the projected-block CTAs (wave-quantisation heuristic below)
+    int upd_tiles = 8;            // 128-column tiles per update CTA (same)
+    int solve_split = 0;          // 1 = two-CTA cluster per pair in the inner solve (latency layout)
     long max_ld = 0;
     int idx[512];                 // indices (into the caller's arrays) of this group's matrices
     size_t off_bmats = 0, off_bindex = 0, off_pairmat = 0, off_partoff = 0, off_state = 0, off_ubuf = 0,
-           off_partial = 0, off_perm = 0, off_lam = 0, off_x = 0;
+           off_partial = 0, off_perm = 0, off_lam = 0, off_x = 0, off_rotlog = 0, off_rotflag = 0;
 };
 struct EighPlan {
     int n_direct = 0, n_block = 0, ngroups = 0;
@@ -874,6 +968,19 @@ static int env_int(const char* name, int dflt) {
 }
 
 static int bj_npad(int n) { return cdiv(n, BJ_B) * BJ_B; }
+
+// SM count of the current device (148 on B200; also the fallback when no device is visible, e.g. a
+// workspace-size query in a CPU-only process)
+static int sm_count_cached() {
+    static int sms = 0;
+    if (sms == 0) {
+        int dev = 0, v = 0;
+        if (cudaGetDevice(&dev) == cudaSuccess &&
+            cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && v > 0) sms = v;
+        else { sms = 148; (void)cudaGetLastError(); }
+    }
+    return sms;
+}
 
 static bool make_plan(const int32_t* n, int count, EighPlan& pl) {
     // block-path matrices, largest first (stable), dealt to the least-loaded group
@@ -913,12 +1020,53 @@ static bool make_plan(const int32_t* n, int count, EighPlan& pl) {
     for (int k = 0; k < pl.ngroups; ++k) {
         GroupPlan& g = pl.g[k];
         size_t x_bytes = 0, part_floats = 0, lam_floats = 0, perm_ints = 0;
+        // Launch shapes that fill whole waves.  Both kernels are latency-bound per CTA, so the time of a launch is
+        // (CTAs an SM has to run one after the other) x (length of one CTA):
+        //   projected block: 3 CTAs / SM resident, one CTA = kchunk / 32 k-slabs + ~3 slabs of set-up / drain;
+        //   update         : 1 CTA / SM, one CTA = upd_tiles tiles + ~0.8 tile of set-up (U staging, pipeline fill).
+        // The heuristics apply when this group has the GPU (nearly) to itself: a single group, or one whose n^3 load
+        // dominates the call (one big factor per rank in multi-GPU runs).  With several balanced groups in flight
+        // the kernels of the others fill the gaps and the defaults (largest chunks, least set-up work) are best.
+        {
+            const int sms = sm_count_cached();
+            const int kc_env = env_int("KFACB_H_KCHUNK", 0), ut_env = env_int("KFACB_UPD_TILES", 0);
+            const int ss_env = env_int("KFACB_SOLVE_SPLIT", -1);
+            double total_load = 0;
+            for (int q = 0; q < pl.ngroups; ++q) total_load += load[q];
+            const bool alone = pl.ngroups == 1 || load[k] >= 0.6 * total_load;
+            long pairs = 0;
+            for (int a = 0; a < g.nb; ++a) pairs += (bj_npad(n[g.idx[a]]) / BJ_B + 1) / 2;
+            g.solve_split = alone && 2 * pairs <= sms;       // the pairs cannot fill the SMs: two SMs per pair
+            if (ss_env >= 0) g.solve_split = ss_env != 0;
+            double best = 1e300;
+            for (int c = BJ_KCHUNK; alone && c >= 256; c -= 128) {
+                long ctas = 0;
+                for (int a = 0; a < g.nb; ++a) {
+                    const int np = bj_npad(n[g.idx[a]]);
+                    ctas += (long)((np / BJ_B + 1) / 2) * cdiv(np, c);
+                }
+                const double cost = (double)cdiv(ctas, 3L * sms) * (c / 32 + 3);
+                if (cost < best) { best = cost; g.kchunk = c; }
+            }
+            if (kc_env >= 32 && kc_env <= BJ_KCHUNK && kc_env % 32 == 0) g.kchunk = kc_env;
+            best = 1e300;
+            for (int t = 16; alone && t >= 4; --t) {
+                long ctas = 0;
+                for (int a = 0; a < g.nb; ++a) {
+                    const int np = bj_npad(n[g.idx[a]]);
+                    ctas += (long)((np / BJ_B + 1) / 2) * cdiv(2 * np / TILE, t);
+                }
+                const double cost = (double)cdiv(ctas, (long)sms) * (t + 0.8);
+                if (cost < best) { best = cost; g.upd_tiles = t; }
+            }
+            if (ut_env > 0) g.upd_tiles = ut_env;
+        }
         for (int a = 0; a < g.nb; ++a) {
             const int nn = n[g.idx[a]];
             const int np = bj_npad(nn);
             const int nblk = np / BJ_B;
             const int p = (nblk + 1) & ~1;
-            const int ks = cdiv(np, BJ_KCHUNK);
+            const int ks = cdiv(np, g.kchunk);
             g.total_pairs += p / 2;
             if (ks > g.max_ksplit) g.max_ksplit = ks;
             if ((p - 1) * 64 > g.max_rounds) g.max_rounds = (p - 1) * 64;   // hard cap; the device-side sweep limit ends earlier
@@ -935,6 +1083,8 @@ static bool make_plan(const int32_t* n, int count, EighPlan& pl) {
         g.off_partoff = take(sizeof(long) * (size_t)(g.nb + 1));
         g.off_state = take(sizeof(BjState) * (size_t)(g.nb + 1));
         g.off_ubuf = take(sizeof(float) * (size_t)g.total_pairs * BJ_M * BJ_M);
+        g.off_rotlog = take(sizeof(float4) * (size_t)g.total_pairs * SOLVE_LOG_STRIDE);
+        g.off_rotflag = take(sizeof(int) * (size_t)(g.total_pairs + 1));
         g.off_partial = take(sizeof(float) * part_floats);
         g.off_perm = take(sizeof(int) * perm_ints);
         g.off_lam = take(sizeof(float) * lam_floats);
@@ -979,9 +1129,33 @@ struct GroupRun {
     BjState* dstate = nullptr;
     float* ubuf = nullptr;
     float* partial = nullptr;
+    float4* rotlog = nullptr;
+    int* rotflag = nullptr;
+    int epoch = 0;                // solve launches so far (the rotation-log flags are monotonic in it)
     cudaStream_t st = nullptr;
     bool done = false;
 };
+
+// one round of inner eigenproblems for every pair of the group (layout chosen in make_plan)
+static cudaError_t launch_solve(GroupRun& gr, const GroupPlan& gp, int round, int full_inner, cudaStream_t st) {
+    const int epoch = ++gr.epoch;
+    if (!gp.solve_split) {
+        bj_solve_kernel<false><<<gp.total_pairs, SolveCfg<false>::THREADS, SolveCfg<false>::SMEM, st>>>(
+            gr.dm, gr.dpm, gr.dstate, round, gr.partial, gr.dpoff, gr.ubuf, gr.rotlog, gr.rotflag, epoch, full_inner);
+        return cudaGetLastError();
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * gp.total_pairs);
+    cfg.blockDim = dim3(SolveCfg<true>::THREADS);
+    cfg.dynamicSmemBytes = SolveCfg<true>::SMEM;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, bj_solve_kernel<true>, gr.dm, gr.dpm, (BjState*)gr.dstate, round,
+                              (const float*)gr.partial, gr.dpoff, gr.ubuf, gr.rotlog, gr.rotflag, epoch, full_inner);
+}
 
 }  // namespace kfacb
 
@@ -1061,13 +1235,12 @@ extern "C" int kfacb_eigh_batched(const int32_t* n, int32_t count,
     for (int i = 0; i < count; ++i)
         if (n[i] > DIRECT_MAX_N) KFACB_REQUIRE(M[i] && Q[i] && d[i], "matrix %d: null pointer", i);
     const bool prof = env_int("KFACB_PROFILE", 0) != 0;
-    const int inner_sweeps = env_int("KFACB_INNER_SWEEPS", BJ_INNER_SWEEPS);   // tuning knobs
     const int full_inner = env_int("KFACB_FULL_INNER", 0);                     // 1 = full inner tournament every visit
     const int max_sweeps = env_int("KFACB_MAX_SWEEPS", BJ_MAX_SWEEPS);
-    const int upd_g = max(1, env_int("KFACB_UPD_TILES", 8));                   // 128-column tiles per update CTA
     KFACB_CHECK_CUDA(cudaFuncSetAttribute(bj_h_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tcg::SMEM));
     KFACB_CHECK_CUDA(cudaFuncSetAttribute(bj_update_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, UPD_SMEM));
-    KFACB_CHECK_CUDA(cudaFuncSetAttribute(bj_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SOLVE_SMEM));
+    KFACB_CHECK_CUDA(cudaFuncSetAttribute(bj_solve_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SolveCfg<false>::SMEM));
+    KFACB_CHECK_CUDA(cudaFuncSetAttribute(bj_solve_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SolveCfg<true>::SMEM));
 
     const int G = pl.ngroups;
     GroupRun run[MAX_GROUPS];
@@ -1092,7 +1265,7 @@ extern "C" int kfacb_eigh_batched(const int32_t* n, int32_t count,
             b.X = (float*)(ws + xo); xo += align_up((size_t)b.n_pad * 2 * b.n_pad * sizeof(float), 256);
             b.lam = (float*)(ws + lo); b.nrm = b.lam + b.n_pad; lo += 2 * (size_t)b.n_pad * sizeof(float);
             b.perm = (int*)(ws + po); po += (size_t)b.n_pad * sizeof(int);
-            b.pair_begin = pair; b.ksplit = cdiv(b.n_pad, BJ_KCHUNK);
+            b.pair_begin = pair; b.kchunk = gp.kchunk; b.ksplit = cdiv(b.n_pad, gp.kchunk);
             // few blocks = short sweeps and little quadratic tail: ask for more before stopping (these are cheap)
             b.tol_conv = 1e-6f * (float)env_int("KFACB_CONV_TOL_E6", b.p >= 16 ? 100 : 20);
             hpoff[a] = partial_off;
@@ -1105,8 +1278,12 @@ extern "C" int kfacb_eigh_batched(const int32_t* n, int32_t count,
         cudaError_t e3 = cudaMemcpyAsync(ws + gp.off_partoff, hpoff, sizeof(long) * gp.nb, cudaMemcpyHostToDevice, gr.st);
         cudaError_t e4 = cudaMemcpyAsync(ws + gp.off_pairmat, hpm, sizeof(int) * gp.total_pairs, cudaMemcpyHostToDevice, gr.st);
         cudaError_t e5 = cudaMemsetAsync(ws + gp.off_state, 0, sizeof(BjState) * gp.nb, gr.st);
+        cudaError_t e6 = cudaMemsetAsync(ws + gp.off_rotflag, 0, sizeof(int) * (gp.total_pairs + 1), gr.st);
         delete[] hidx; delete[] hpoff; delete[] hpm;
         KFACB_CHECK_CUDA(e1); KFACB_CHECK_CUDA(e2); KFACB_CHECK_CUDA(e3); KFACB_CHECK_CUDA(e4); KFACB_CHECK_CUDA(e5);
+        KFACB_CHECK_CUDA(e6);
+        gr.rotlog = (float4*)(ws + gp.off_rotlog);
+        gr.rotflag = (int*)(ws + gp.off_rotflag);
         gr.dm = (const BjMat*)(ws + gp.off_bmats);
         gr.dpm = (const int*)(ws + gp.off_pairmat);
         gr.dpoff = (const long*)(ws + gp.off_partoff);
@@ -1143,9 +1320,9 @@ extern "C" int kfacb_eigh_batched(const int32_t* n, int32_t count,
             if (prof) cudaEventRecord(pev[0], gr.st);
             bj_h_tc_kernel<<<dim3(gp.max_ksplit, gp.total_pairs), tcg::THREADS, tcg::SMEM, gr.st>>>(gr.dm, gr.dpm, gr.dstate, r, gr.partial, gr.dpoff);
             if (prof) cudaEventRecord(pev[1], gr.st);
-            bj_solve_kernel<<<gp.total_pairs, SOLVE_THREADS, SOLVE_SMEM, gr.st>>>(gr.dm, gr.dpm, gr.dstate, r, gr.partial, gr.dpoff, gr.ubuf, inner_sweeps, full_inner);
+            KFACB_CHECK_CUDA(launch_solve(gr, gp, r, full_inner, gr.st));
             if (prof) cudaEventRecord(pev[2], gr.st);
-            bj_update_tc_kernel<<<dim3(cdiv(col_tiles, upd_g), gp.total_pairs), UPD_THREADS, UPD_SMEM, gr.st>>>(gr.dm, gr.dpm, gr.dstate, r, gr.ubuf, upd_g);
+            bj_update_tc_kernel<<<dim3(cdiv(col_tiles, gp.upd_tiles), gp.total_pairs), UPD_THREADS, UPD_SMEM, gr.st>>>(gr.dm, gr.dpm, gr.dstate, r, gr.ubuf, gp.upd_tiles);
             if (prof) {          // KFACB_PROFILE=1: per-kernel time of every round (debug only: synchronises each round)
                 cudaEventRecord(pev[3], gr.st);
                 cudaEventSynchronize(pev[3]);
@@ -1174,8 +1351,9 @@ extern "C" int kfacb_eigh_batched(const int32_t* n, int32_t count,
         if (!any_active) break;
     }
     if (prof) {
-        fprintf(stderr, "[kfacb eigh profile] matrices=%d pairs=%d rounds=%d  H %.1f ms  solve %.1f ms  update %.1f ms\n",
-                pl.g[0].nb, pl.g[0].total_pairs, prounds, ptime[0], ptime[1], ptime[2]);
+        fprintf(stderr, "[kfacb eigh profile] matrices=%d pairs=%d rounds=%d  H %.1f ms  solve %.1f ms  update %.1f ms"
+                "  (kchunk %d, tiles/CTA %d, split solve %d)\n",
+                pl.g[0].nb, pl.g[0].total_pairs, prounds, ptime[0], ptime[1], ptime[2], pl.g[0].kchunk, pl.g[0].upd_tiles, pl.g[0].solve_split);
         for (int k = 0; k < 4; ++k) cudaEventDestroy(pev[k]);
         g_profile[0] = prounds; g_profile[1] = ptime[0]; g_profile[2] = ptime[1]; g_profile[3] = ptime[2];
         g_profile[4] = pbytes[0]; g_profile[5] = pbytes[1]; g_profile[6] = pl.g[0].nb; g_profile[7] = pl.g[0].total_pairs;
@@ -1219,8 +1397,8 @@ extern "C" int kfacb_eigh_batched(const int32_t* n, int32_t count,
             const int col_tiles = cdiv(gp.max_ld, TILE);
             for (int r = 0; r < pmax - 1; ++r) {
                 bj_h_tc_kernel<<<dim3(gp.max_ksplit, gp.total_pairs), tcg::THREADS, tcg::SMEM, gs>>>(gr.dm, gr.dpm, gr.dstate, r, gr.partial, gr.dpoff);
-                bj_solve_kernel<<<gp.total_pairs, SOLVE_THREADS, SOLVE_SMEM, gs>>>(gr.dm, gr.dpm, gr.dstate, r, gr.partial, gr.dpoff, gr.ubuf, inner_sweeps, full_inner);
-                bj_update_tc_kernel<<<dim3(cdiv(col_tiles, upd_g), gp.total_pairs), UPD_THREADS, UPD_SMEM, gs>>>(gr.dm, gr.dpm, gr.dstate, r, gr.ubuf, upd_g);
+                KFACB_CHECK_CUDA(launch_solve(gr, gp, r, full_inner, gs));
+                bj_update_tc_kernel<<<dim3(cdiv(col_tiles, gp.upd_tiles), gp.total_pairs), UPD_THREADS, UPD_SMEM, gs>>>(gr.dm, gr.dpm, gr.dstate, r, gr.ubuf, gp.upd_tiles);
                 bool boundary = false;
                 for (int a = 0; a < gp.nb && !boundary; ++a) boundary = ((r + 1) % (gr.hm[a].p - 1)) == 0;
                 if (boundary) { bj_check_kernel<<<1, 256, 0, gs>>>(gr.dm, gr.dstate, gp.nb, r, max_sweeps, rt->d_active + k, 1); count_launch(1); }

@@ -1,6 +1,6 @@
 """GPU probe: time kfacb_eigh_batched on Wishart matrices of the ResNet-50 factor
 sizes and report sweeps / accuracy.  Tuning knobs come from the environment
-(KFACB_INNER_SWEEPS, KFACB_MAX_SWEEPS).   python tools/eigh_probe.py 4608 [2304 ...]"""
+(KFACB_MAX_SWEEPS, KFACB_SOLVE_SPLIT, KFACB_H_KCHUNK, KFACB_UPD_TILES, KFACB_PROFILE).   python tools/eigh_probe.py 4608 [2304 ...]"""
 import os
 import sys
 import time
