@@ -8,6 +8,7 @@
 // products, the preconditioning GEMM chain and the blocked inverse.
 #pragma once
 #include <cuda_runtime.h>
+#include <type_traits>
 #include <stdint.h>
 #include <stdio.h>
 #include "kfacb.h"
@@ -166,10 +167,18 @@ struct LdMnContig {
 // generic GEMM kernel:  C(m, n) = epi(m, n, sum_k A(m,k) B(n,k))
 // grid = (tiles_n, tiles_m, batch); the functors may use blockIdx.z.
 // -------------------------------------------------------------------------
+// An epilogue may declare `static constexpr bool UPPER_ONLY = true` for a symmetric product: only the tiles on
+// or above the diagonal are computed and the epilogue mirrors the off-diagonal ones itself.
+template <class E, class = void>
+struct epi_upper_only : std::false_type {};
+template <class E>
+struct epi_upper_only<E, std::void_t<decltype(E::UPPER_ONLY)>> : std::integral_constant<bool, E::UPPER_ONLY> {};
+
 template <class LA, class LB, class Epi>
 __global__ void __launch_bounds__(GEMM_THREADS, 2)
 gemm_kernel(LA la, LB lb, Epi epi, int M, int N, int K) {
     __shared__ GemmSmem sm;
+    if (epi_upper_only<Epi>::value && blockIdx.x < blockIdx.y) return;
     const int m0 = blockIdx.y * TILE, n0 = blockIdx.x * TILE;
     float acc[8][8];
 #pragma unroll

@@ -916,9 +916,11 @@ __global__ void bj_store_sweeps_kernel(const BjState* state, const int* out_inde
 // Newton-Schulz re-orthogonalisation of the accumulated eigenvector rows:
 //   E = V V^T - I  (into the W half of X),  V <- V - 0.5 E V  (via the Q buffer)
 struct EpiGramMinusI {
+    static constexpr bool UPPER_ONLY = true;      // V V^T is symmetric: tiles above the diagonal are mirrored
     float* X; long ld;
     __device__ __forceinline__ void operator()(int m, int n, float v) const {
         X[(long)m * ld + n] = v - (m == n ? 1.f : 0.f);
+        if (m / TILE != n / TILE) X[(long)n * ld + m] = v;
     }
 };
 struct EpiNsUpdate {
