@@ -30,8 +30,7 @@ constexpr int BJ_B = 64;              // rows per block
 constexpr int BJ_M = 2 * BJ_B;        // rows per pair = size of the inner eigenproblem (= TILE)
 constexpr int BJ_KCHUNK = 512;        // largest split-K chunk of the projected-block GEMM (the host picks 256/384/512)
 static_assert(BJ_M == TILE, "a pair is one 128-row GEMM tile");
-constexpr int BJ_MAX_SWEEPS = 16;
-    // cap of Jacobi sweeps on the 64x64 Gram per visit
+constexpr int BJ_MAX_SWEEPS = 16;     // cap of outer sweeps (KFACB_MAX_SWEEPS)
 constexpr int DIRECT_MAX_N = 128;
 
 struct BjMat {

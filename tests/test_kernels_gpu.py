@@ -146,6 +146,37 @@ def test_eigh_batched_mixed_sizes(eng):
     assert torch.all(sw > 0)
 
 
+@pytest.mark.parametrize('knobs', [
+    {'KFACB_SOLVE_SPLIT': '0'}, {'KFACB_SOLVE_SPLIT': '1'},
+    {'KFACB_H_KCHUNK': '256', 'KFACB_UPD_TILES': '5'}, {'KFACB_H_KCHUNK': '512', 'KFACB_UPD_TILES': '16'},
+], ids=lambda k: ','.join('%s=%s' % (a[6:], b) for a, b in k.items()))
+def test_eigh_launch_shapes_do_not_change_the_result(eng, monkeypatch, knobs):
+    """The host picks the solve layout (one CTA / a 2-CTA cluster per pair), the k-chunk of the projected-block
+    GEMM and the tiles per update CTA from the group's size; every choice must give the same decomposition."""
+    gen = torch.Generator().manual_seed(77)
+    ns = [641, 300]
+    mats = [(_spectra(n, 'lowrank', gen)).float().to(DEV).contiguous() for n in ns]
+
+    def run():
+        Qs = [torch.empty(n, n, device=DEV) for n in ns]
+        ds = [torch.empty(n, device=DEV) for n in ns]
+        sw = torch.zeros(len(ns), dtype=torch.int32, device=DEV)
+        eng.eigh(mats, Qs, ds, 1e-10, sw)
+        return Qs, ds, sw
+
+    _, d_ref, sw_ref = run()
+    for k, v in knobs.items():
+        monkeypatch.setenv(k, v)
+    Qs, ds, sw = run()
+    for M, Q, d, d0 in zip(mats, Qs, ds, d_ref):
+        scale = d0.abs().max().item()
+        assert (d - d0).abs().max().item() <= 2e-6 * scale
+        QQ, dd = Q.double().cpu(), d.double().cpu()
+        assert ((QQ * dd) @ QQ.t() - M.double().cpu()).norm() <= 4e-5 * M.double().norm().cpu()
+        assert (QQ.t() @ QQ - torch.eye(M.shape[0], dtype=torch.float64)).abs().max().item() < 2e-5
+    assert torch.all((sw - sw_ref).abs() <= 1)
+
+
 @pytest.mark.parametrize('dims', [(5, 3), (64, 10), (65, 64), (200, 130), (513, 40), (1153, 128)], ids=str)
 def test_pi_damped_inverse(eng, dims):
     nA, nG = dims
