@@ -26,6 +26,9 @@ def graded(n, gen, dev):
 def main():
     dev = torch.device('cuda:0')
     eng = NativeEngine(dev)
+    if os.environ.get('KFACB_PROBE_LIB'):        # evaluate a variant library (tools/experiments/build_variants.py)
+        from kfac_pytorch_b200.native import load_library
+        eng.lib = load_library(os.environ['KFACB_PROBE_LIB'])
     ns = [int(x) for x in sys.argv[1:]] or [4608]
     gen = torch.Generator(device=dev).manual_seed(0)
     if os.environ.get('PROBE_GRADED'):
