@@ -817,8 +817,12 @@ __global__ void bj_check_kernel(const BjMat* mats, BjState* state, int nmat, int
         }
     }
     __syncthreads();
-    if (threadIdx.x == 0) *host_active = active;
+    if (threadIdx.x == 0 && host_active) *host_active = active;
 }
+
+// arms the host-visible progress flag of a group IN STREAM ORDER (a host store would race with the still queued
+// kernels of the previous call, which write the same flag)
+__global__ void bj_arm_kernel(volatile int* host_active) { *host_active = 1; }
 
 // lam_i = (v_i . y_i) / (v_i . v_i) with y_i = A v_i stored in the W half.  one warp per row
 __global__ void bj_rayleigh_kernel(const BjMat* mats) {
@@ -1291,7 +1295,7 @@ extern "C" int kfacb_eigh_batched(const int32_t* n, int32_t count,
         gr.dstate = (BjState*)(ws + gp.off_state);
         gr.ubuf = (float*)(ws + gp.off_ubuf);
         gr.partial = (float*)(ws + gp.off_partial);
-        rt->h_active[k] = 1;
+        bj_arm_kernel<<<1, 1, 0, gr.st>>>(rt->d_active + k);
         bj_init_kernel<<<dim3(4 * sm_count(), gp.nb), 256, 0, gr.st>>>(gr.dm, gr.dstate);
         KFACB_CHECK_LAUNCH();
     }
@@ -1402,7 +1406,7 @@ extern "C" int kfacb_eigh_batched(const int32_t* n, int32_t count,
                 bj_update_tc_kernel<<<dim3(cdiv(col_tiles, gp.upd_tiles), gp.total_pairs), UPD_THREADS, UPD_SMEM, gs>>>(gr.dm, gr.dpm, gr.dstate, r, gr.ubuf, gp.upd_tiles);
                 bool boundary = false;
                 for (int a = 0; a < gp.nb && !boundary; ++a) boundary = ((r + 1) % (gr.hm[a].p - 1)) == 0;
-                if (boundary) { bj_check_kernel<<<1, 256, 0, gs>>>(gr.dm, gr.dstate, gp.nb, r, max_sweeps, rt->d_active + k, 1); count_launch(1); }
+                if (boundary) { bj_check_kernel<<<1, 256, 0, gs>>>(gr.dm, gr.dstate, gp.nb, r, max_sweeps, nullptr, 1); count_launch(1); }
                 count_launch(3);
             }
             KFACB_CHECK_LAUNCH();

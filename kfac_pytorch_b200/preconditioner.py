@@ -42,6 +42,14 @@ def _static_desc(module) -> LayerDesc:
     """Descriptor with the batch-independent fields (enough for dA/dG)."""
     d = LayerDesc()
     if module.__class__.__name__ == 'Conv2d':
+        # the reference's ComputeA/_get_grad assume dense convolutions (kfac/utils.py:33-54,85-94): a grouped conv
+        # fails there with a matmul shape error; here it would index past the gradient buffer, so refuse it loudly
+        if getattr(module, 'groups', 1) != 1:
+            raise NotImplementedError('KFAC: Conv2d with groups=%d is not supported' % module.groups)
+        if tuple(getattr(module, 'dilation', (1, 1))) != (1, 1):
+            raise NotImplementedError('KFAC: dilated Conv2d is not supported')
+        if getattr(module, 'padding_mode', 'zeros') != 'zeros':
+            raise NotImplementedError('KFAC: Conv2d padding_mode=%r is not supported' % module.padding_mode)
         d.kind = KFACB_CONV2D
         d.in_c, d.out_c = module.in_channels, module.out_channels
         d.kh, d.kw = module.kernel_size
@@ -273,8 +281,12 @@ class KFAC(optim.Optimizer):
             a, g = _prep(self.m_a[m]), _prep(self.m_g[m])
             d = _full_desc(m, a, g)
             if m not in self.m_A:
-                self.m_A[m] = torch.empty(d.dA, d.dA, dtype=torch.float32, device=a.device)
-                self.m_G[m] = torch.empty(d.dG, d.dG, dtype=torch.float32, device=a.device)
+                # step 0: the kernel overwrites with the identity-initialised EMA (first_step).  Later (a layer whose
+                # factors were not restored from a checkpoint): start from the identity like step 0 did, never from
+                # uninitialised memory
+                mk = torch.empty if self.steps == 0 else (lambda n, _n, **kw: torch.eye(n, **kw))
+                self.m_A[m] = mk(d.dA, d.dA, dtype=torch.float32, device=a.device)
+                self.m_G[m] = mk(d.dG, d.dG, dtype=torch.float32, device=a.device)
             descs.append(d); a_l.append(a); g_l.append(g)
             A_l.append(self.m_A[m]); G_l.append(self.m_G[m])
         eng.factor_update(descs, a_l, g_l, A_l, G_l, self.factor_decay, self.steps == 0)
@@ -394,6 +406,10 @@ class KFAC(optim.Optimizer):
             if wg.dtype != torch.float32 or not wg.is_contiguous() or \
                     (bg is not None and (bg.dtype != torch.float32 or not bg.is_contiguous())):
                 raise RuntimeError('%s: gradients must be contiguous float32' % self.module_names[i])
+            st = self._static[i]
+            if wg.numel() != st.dG * (st.dA - st.has_bias) or (bg is not None and bg.numel() != st.dG):
+                raise RuntimeError('%s: gradient has %d elements, the layer geometry says %d'
+                                   % (self.module_names[i], wg.numel(), st.dG * (st.dA - st.has_bias)))
             w.append(wg); b.append(bg)
         return w, b
 
@@ -448,7 +464,11 @@ class KFAC(optim.Optimizer):
         (SURVEY.md section 5 / 8f rank 4); ``torch.save`` this next to ``state_dict()``."""
         def pack(d):
             return {i: d[m].detach().to("cpu", copy=True) for i, m in enumerate(self.modules) if m in d}
+        if self.module_ranks is None:
+            self.schedule_module_ranks()
         return dict(variant=self.variant, steps=self.steps, world_size=backend.comm.size(),
+                    rank=backend.comm.rank(), partition=self.partition,
+                    owners=[self.module_ranks[m][0] for m in self.modules],
                     m_A=pack(self.m_A), m_G=pack(self.m_G), m_QA=pack(self.m_QA), m_QG=pack(self.m_QG),
                     m_dA=pack(self.m_dA), m_dG=pack(self.m_dG), m_inv_A=pack(self.m_inv_A),
                     m_inv_G=pack(self.m_inv_G))
@@ -456,6 +476,25 @@ class KFAC(optim.Optimizer):
     def load_kfac_state_dict(self, state):
         if state['variant'] != self.variant or state['world_size'] != backend.comm.size():
             raise ValueError('K-FAC state was saved for variant=%s world_size=%d' % (state['variant'], state['world_size']))
+        if self.module_ranks is None:
+            self.schedule_module_ranks()
+        me = backend.comm.rank()
+        # DP variants keep per-rank state (only the owned layers): every rank must load the state IT saved, with the
+        # same ownership map; loading rank 0's file on rank 1 would silently drop rank 1's factors
+        if self.is_dp:
+            owners = [self.module_ranks[m][0] for m in self.modules]
+            if 'owners' in state and list(state['owners']) != owners:
+                raise ValueError('K-FAC state was saved with a different layer->rank ownership map')
+            if 'rank' in state and int(state['rank']) != me and backend.comm.size() > 1:
+                raise ValueError('K-FAC state of rank %d loaded on rank %d: the DP variants keep per-rank state, '
+                                 'save and load one file per rank' % (int(state['rank']), me))
+            if int(state['steps']) > 0:
+                need = ['m_A', 'm_G'] + (['m_QA', 'm_QG', 'm_dA', 'm_dG'] if self.uses_eigen else ['m_inv_A', 'm_inv_G'])
+                for i, o in enumerate(owners):
+                    if o == me:
+                        for name in need:
+                            if i not in state[name] and str(i) not in state[name]:
+                                raise ValueError('K-FAC state lacks %s of owned layer %d' % (name, i))
         dev = self._device()
         for name in ('m_A', 'm_G', 'm_QA', 'm_QG', 'm_dA', 'm_dG', 'm_inv_A', 'm_inv_G'):
             tgt = getattr(self, name)
