@@ -23,6 +23,8 @@
 #include "common.cuh"
 #include "tc_gemm.cuh"
 #include "tc.cuh"
+#include "jacobi_smem.cuh"
+#include "eigh_trd.cuh"
 
 namespace kfacb {
 
@@ -31,7 +33,6 @@ constexpr int BJ_M = 2 * BJ_B;        // rows per pair = size of the inner eigen
 constexpr int BJ_KCHUNK = 512;        // largest split-K chunk of the projected-block GEMM (the host picks 256/384/512)
 static_assert(BJ_M == TILE, "a pair is one 128-row GEMM tile");
 constexpr int BJ_MAX_SWEEPS = 16;     // cap of outer sweeps (KFACB_MAX_SWEEPS)
-constexpr int DIRECT_MAX_N = 128;
 
 struct BjMat {
     float* X;             // n_pad x 2 n_pad work array
@@ -57,93 +58,6 @@ struct BjState {          // per matrix, device
     float off2;           // sum over the pairs visited this sweep of ||cross block of H||_F^2
     float norm2;          // ||A||_F^2
 };
-
-// ---------------------------------------------------------------------------
-// two-sided cyclic Jacobi on an m x m symmetric matrix in shared memory
-// (m even, pitch P odd; M_CT = m at compile time or 0).  On exit S is diagonal (to tolerance) and U holds the
-// accumulated rotations (columns = eigenvectors of the input).  Returns the
-// number of sweeps executed; *sig_out = 1 if any rotated element exceeded sig_abs.
-// All threads of the CTA must call it.
-// ---------------------------------------------------------------------------
-template <int M_CT>
-__device__ int jacobi_smem(float* S, float* U, int m_rt, int P, float tol_rel, float abs_thr,
-                           float sig_abs, int max_sweeps, int* sig_out) {
-    __shared__ float s_c[DIRECT_MAX_N / 2], s_s[DIRECT_MAX_N / 2];
-    __shared__ int s_p[DIRECT_MAX_N / 2], s_q[DIRECT_MAX_N / 2];
-    __shared__ int s_flag, s_sig;
-    const int m = M_CT ? M_CT : m_rt;            // compile-time size for the 64x64 inner problem
-    const int tid = threadIdx.x, nt = blockDim.x;
-    const int half = m >> 1, mm1 = m - 1;
-    if (tid == 0) s_sig = 0;
-    int sweeps = 0;
-    int prev_p = -1, prev_q = -1;
-    for (int sw = 0; sw < max_sweeps; ++sw) {
-        __syncthreads();
-        if (tid == 0) s_flag = 0;
-        __syncthreads();
-        for (int r = 0; r < mm1; ++r) {
-            if (tid < half) {
-                if (prev_p >= 0) { S[prev_p * P + prev_q] = 0.f; S[prev_q * P + prev_p] = 0.f; prev_p = -1; }
-                int p, q;
-                if (tid == 0) { p = mm1; q = r; }
-                else { p = r + tid; if (p >= mm1) p -= mm1; q = r - tid; if (q < 0) q += mm1; }
-                if (p > q) { const int t = p; p = q; q = t; }
-                const float app = S[p * P + p], aqq = S[q * P + q], apq = S[p * P + q];
-                float c = 1.f, s = 0.f;
-                const float mag = fabsf(apq);
-                const float ref = sqrtf(fabsf(app) * fabsf(aqq));
-                if (mag > tol_rel * ref && mag > abs_thr) {
-                    // Rutishauser's stable formulas; correctly rounded sqrt/div keep c^2+s^2 = 1 to ~1 ulp
-                    const float tau = (aqq - app) / (2.f * apq);
-                    const float t = (tau >= 0.f ? 1.f : -1.f) / (fabsf(tau) + sqrtf(1.f + tau * tau));
-                    c = 1.f / sqrtf(1.f + t * t);
-                    s = t * c;
-                    s_flag = 1;
-                    if (mag > sig_abs) s_sig = 1;
-                    prev_p = p; prev_q = q;
-                }
-                s_c[tid] = c; s_s[tid] = s; s_p[tid] = p; s_q[tid] = q;
-            }
-            __syncthreads();
-            // column rotations: S <- S J, U <- U J   (lanes walk the row index: conflict-free, P odd)
-            for (int e = tid; e < half * m; e += nt) {
-                const int k = e / m, i = e - k * m;
-                const float s = s_s[k];
-                if (s != 0.f) {
-                    const float c = s_c[k];
-                    const int p = s_p[k], q = s_q[k];
-                    float x = S[i * P + p], y = S[i * P + q];
-                    S[i * P + p] = c * x - s * y;
-                    S[i * P + q] = s * x + c * y;
-                    x = U[i * P + p]; y = U[i * P + q];
-                    U[i * P + p] = c * x - s * y;
-                    U[i * P + q] = s * x + c * y;
-                }
-            }
-            __syncthreads();
-            // row rotations: S <- J^T S
-            for (int e = tid; e < half * m; e += nt) {
-                const int k = e / m, j = e - k * m;
-                const float s = s_s[k];
-                if (s != 0.f) {
-                    const float c = s_c[k];
-                    const int p = s_p[k], q = s_q[k];
-                    const float x = S[p * P + j], y = S[q * P + j];
-                    S[p * P + j] = c * x - s * y;
-                    S[q * P + j] = s * x + c * y;
-                }
-            }
-            __syncthreads();
-        }
-        ++sweeps;
-        if (!s_flag) break;
-    }
-    __syncthreads();
-    if (tid < half && prev_p >= 0) { S[prev_p * P + prev_q] = 0.f; S[prev_q * P + prev_p] = 0.f; }
-    __syncthreads();
-    if (sig_out) *sig_out = s_sig;
-    return sweeps;
-}
 
 // ---------------------------------------------------------------------------
 // direct path: n <= 128, one CTA per matrix
@@ -1172,11 +1086,36 @@ extern "C" int kfacb_eigh_last_profile(double* out8) {
     return KFACB_OK;
 }
 
+// n > 128: tridiagonalisation + divide and conquer (eigh_trd.cu / eigh_dc.cu) unless KFACB_EIGH_ALGO=jacobi asks
+// for the round-1 block-Jacobi path below (kept for A/B comparisons)
+static bool use_block_jacobi() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("KFACB_EIGH_ALGO"); v = (e && (e[0] == 'j' || e[0] == 'J')) ? 1 : 0; }
+    return v == 1;
+}
+static size_t direct_tables_bytes(int n_direct) {
+    return align_up(sizeof(DirectMat) * (size_t)(n_direct + 1), 256) + align_up(sizeof(int) * (size_t)(n_direct + 1), 256);
+}
+static int collect_blocked(const int32_t* n, int count, int* idx) {
+    int nb = 0;
+    for (int i = 0; i < count; ++i) if (n[i] > DIRECT_MAX_N) idx[nb++] = i;
+    return nb;
+}
+
 extern "C" size_t kfacb_eigh_workspace_bytes(const int32_t* n, int32_t count) {
-    EighPlan* pl = new EighPlan();
-    const bool ok = make_plan(n, count, *pl);
-    const size_t t = ok ? pl->total : 0;
-    delete pl;
+    if (!n || count <= 0) return 256;
+    size_t t = 0;
+    if (use_block_jacobi()) {
+        EighPlan* pl = new EighPlan();
+        const bool ok = make_plan(n, count, *pl);
+        t = ok ? pl->total : 0;
+        delete pl;
+        return t;
+    }
+    int* idx = new int[count];
+    const int nb = collect_blocked(n, count, idx);
+    t = direct_tables_bytes(count - nb) + eigh_tdc_workspace_bytes(n, count, idx, nb) + 256;
+    delete[] idx;
     return t;
 }
 
@@ -1187,6 +1126,45 @@ extern "C" int kfacb_eigh_batched(const int32_t* n, int32_t count,
                                   kfacb_stream_t stream) {
     cudaStream_t st = (cudaStream_t)stream;
     KFACB_REQUIRE(n && M && Q && d && count >= 0, "null argument");
+    if (!use_block_jacobi()) {
+        // direct Jacobi for n <= 128, tridiagonalisation + divide and conquer above; only enqueues work
+        KFACB_REQUIRE(workspace && !((uintptr_t)workspace & 255), "eigh workspace missing or misaligned");
+        for (int i = 0; i < count; ++i)
+            if (n[i] > 0) KFACB_REQUIRE(M[i] && Q[i] && d[i], "matrix %d: null pointer", i);
+        int* idx = new int[count > 0 ? count : 1];
+        struct IdxGuard { int* p; ~IdxGuard() { delete[] p; } } idx_guard{idx};
+        const int nb = collect_blocked(n, count, idx);
+        int n_direct = 0;
+        for (int i = 0; i < count; ++i) n_direct += (n[i] > 0 && n[i] <= DIRECT_MAX_N);
+        const size_t dbytes = direct_tables_bytes(count - nb);
+        if (workspace_bytes < dbytes) { set_error("eigh workspace too small"); return KFACB_ERR_WORKSPACE; }
+        char* ws = (char*)workspace;
+        if (n_direct > 0) {
+            DirectMat* hm = new DirectMat[n_direct];
+            int* hidx = new int[n_direct];
+            int k = 0, nmax = 0;
+            for (int i = 0; i < count; ++i) {
+                if (n[i] <= 0 || n[i] > DIRECT_MAX_N) continue;
+                hm[k] = DirectMat{M[i], Q[i], d[i], n[i]};
+                hidx[k] = i;
+                if (n[i] > nmax) nmax = n[i];
+                ++k;
+            }
+            char* dmats = ws;
+            char* dindex = ws + align_up(sizeof(DirectMat) * (size_t)(count - nb + 1), 256);
+            cudaError_t e1 = cudaMemcpyAsync(dmats, hm, sizeof(DirectMat) * k, cudaMemcpyHostToDevice, st);
+            cudaError_t e2 = cudaMemcpyAsync(dindex, hidx, sizeof(int) * k, cudaMemcpyHostToDevice, st);
+            delete[] hm; delete[] hidx;
+            KFACB_CHECK_CUDA(e1); KFACB_CHECK_CUDA(e2);
+            const int m = (nmax + 1) & ~1;
+            const size_t smem = 2 * (size_t)m * (m + 1) * sizeof(float);
+            KFACB_CHECK_CUDA(cudaFuncSetAttribute(jacobi_direct_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            const int threads = nmax <= 32 ? 128 : (nmax <= 64 ? 256 : 512);
+            jacobi_direct_kernel<<<k, threads, smem, st>>>((const DirectMat*)dmats, eps_floor, sweeps_out, (const int*)dindex);
+            KFACB_CHECK_LAUNCH();
+        }
+        return eigh_tdc_run(n, idx, nb, M, Q, d, eps_floor, sweeps_out, ws + dbytes, workspace_bytes - dbytes, st);
+    }
     EighPlan* plp = new EighPlan();
     struct PlanGuard { EighPlan* p; ~PlanGuard() { delete p; } } plan_guard{plp};
     KFACB_REQUIRE(make_plan(n, count, *plp), "too many matrices in one eigh batch");

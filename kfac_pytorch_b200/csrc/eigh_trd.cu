@@ -1,0 +1,482 @@
+// eigh_trd.cu -- Householder tridiagonalisation A = Q_H T Q_H^T of a BATCH of symmetric fp32 matrices in ONE
+// persistent kernel (first stage of the n > 128 path of kfacb_eigh_batched; replaces the LAPACK ssytrd inside
+// torch.linalg.eigh of the reference, kfac/utils.py:22-25 / kfac_preconditioner_eigen_dp.py:62-75).
+//
+// Why this shape on B200.  The reduction is a chain of n dependent columns; each column needs one symmetric
+// matrix-vector product with the trailing matrix (BLAS-2: 4 m^2 bytes at column j, m = n - j) -- HBM/L2
+// bandwidth and LATENCY bound, nothing for the tensor cores.  So:
+//   * the batch is scheduled on the 148 SMs as TEAMS of CTAs (1 CTA / SM, cooperative launch): a big factor gets a
+//     team sized by a latency + bandwidth cost model, small factors are packed several to a single-CTA team;
+//     all matrices advance concurrently and HBM stays saturated while each chain only pays its own latency;
+//   * inside a team, rows are dealt cyclically (row i -> CTA i mod team), a warp does a whole row of the product
+//     (coalesced float4 ld.global.cg, the reflector in shared memory), and a column costs exactly TWO team
+//     barriers (a release/acquire counter in L2, ~1 us): column+norm | barrier | reflector+product+panel inner
+//     products | barrier.  Everything else that LAPACK's slatrd does with extra synchronisation (w = p - ..v,
+//     the panel corrections V(W^T v) + W(V^T v), v^T p) is algebraically folded so that it needs only the sums
+//     made in the same pass; partial sums go through per-CTA slots and are added in a fixed order
+//     (deterministic, no float atomics);
+//   * updates are delayed LAPACK-style: within a panel of 32 columns the trailing matrix is read only, the
+//     rank-64 update A -= V W^T + W V^T runs once per panel as an exact-fp32 register-tiled SIMT GEMM on 128x128
+//     tiles (K = 64: too skinny to be worth a TMEM round trip; 4/3 n^3 flops in total, < 10 % of the step);
+//   * reflector j is left in the dead row j of the work array (T[j][j+1..n)), K-contiguous, which is exactly the
+//     operand layout the tensor-core back-transformation (eigh_dc.cu) wants.
+// The formulas are pinned by tools/eigh_trd_dc_model.py (same phases in numpy).
+#include <stdlib.h>
+#include "eigh_trd.cuh"
+
+namespace kfacb {
+namespace trd {
+
+constexpr int OP_PITCH = 132;                                   // 128 + 4: float4-aligned, spreads banks
+
+struct __align__(16) Smem {
+    float v[MAXN];                                              // reflector of the current column (absolute index)
+    float op[4][NB][OP_PITCH];                                  // rank-2k update operands: V_I, W_I, W_J, V_J (k-major)
+    float red[3][NWARP][33];
+    float q[72];                                                // team-reduced partial sums: [0,32) W^T v, [32,64) V^T v, [64] v.y, [65] |x|^2
+    float rowV[32], rowW[32];
+    float cw, tau, scale;
+};
+
+__device__ __forceinline__ void team_barrier(unsigned* ctr, unsigned& target, int team) {
+    __syncthreads();
+    if (team > 1) {
+        target += (unsigned)team;
+        if (threadIdx.x == 0) {
+            __threadfence();
+            asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(ctr) : "memory");
+            unsigned v;
+            do {
+                asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
+            } while (v < target);
+            __threadfence();
+        }
+        __syncthreads();
+    }
+}
+
+__device__ __forceinline__ int first_own(int r0, int rank, int team) {
+    int o = rank - r0 % team;
+    if (o < 0) o += team;
+    return r0 + o;
+}
+
+// Team-wide sums of the partials [kbeg, kend): quantity k lives in part[k * TS + rank]; a warp adds the team's
+// slots of one quantity (coalesced, fixed order: identical bits on every CTA).  All threads; ends with a barrier.
+__device__ __forceinline__ void reduce_partials(const Job& jb, Smem& sm, int kbeg, int kend) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int k = kbeg + warp; k < kend; k += NWARP) {
+        float a = 0.f;
+        for (int r = lane; r < jb.team; r += 32) a += __ldcg(jb.part + k * TS + r);
+        a = warp_sum(a);
+        if (lane == 0) sm.q[k] = a;
+    }
+    __syncthreads();
+}
+
+// What finishing column `kc` of W needs, from the reduced sums s = W^T v = q[0..), t = V^T v = q[32..):
+// cw = tau^2 (v.y - 2 s.t) / 2.  With want_row it also finishes W[row_j][kc] redundantly (every CTA needs row j of
+// the panels) and stages rows j of V and W.  Warp 0 only; followed by __syncthreads.
+__device__ __forceinline__ void finish_prologue(const Job& jb, Smem& sm, int kc, int row_j, bool want_row) {
+    const int lane = threadIdx.x & 31;
+    const float s = sm.q[lane], t = sm.q[32 + lane], vy = sm.q[64];
+    const float st = warp_sum(lane < kc ? s * t : 0.f);
+    const float tau = sm.tau;
+    const float cw = 0.5f * tau * tau * (vy - 2.f * st);
+    if (lane == 0) sm.cw = cw;
+    if (want_row) {
+        const float vj = lane <= kc ? __ldcg(jb.Vp + (size_t)row_j * NB + lane) : 0.f;
+        float wj = lane < kc ? __ldcg(jb.Wp + (size_t)row_j * NB + lane) : 0.f;
+        const float dot = warp_sum(lane < kc ? vj * s + wj * t : 0.f);
+        const float yj = __ldcg(jb.y + row_j);
+        const float vlast = __shfl_sync(0xffffffffu, vj, kc);
+        const float wnew = tau * (yj - dot) - cw * vlast;
+        if (lane == kc) wj = wnew;
+        sm.rowV[lane] = vj;
+        sm.rowW[lane] = wj;
+    }
+}
+
+// A[R0.., R0..] -= V W^T + W V^T over the first kc panel columns; tiles of 128x128 dealt to the team
+__device__ void rank2k_update(const Job& jb, Smem& sm, int R0, int kc, int rank) {
+    const int n = jb.n, ldt = jb.ldt;
+    const int mt = n - R0;
+    if (mt <= 0) return;
+    const int nt = (mt + 127) >> 7;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int row4 = 16 * (warp >> 2) + 4 * (lane >> 3);         // 8 x 4 warps, lanes 4 (rows) x 8 (cols)
+    const int col4 = 32 * (warp & 3) + 4 * (lane & 7);
+    const bool aligned = (R0 & 3) == 0;
+    for (int q = rank; q < nt * nt; q += jb.team) {
+        const int ti = q / nt, tj = q - ti * nt;
+        __syncthreads();
+        {
+            const int r = tid >> 3, kq = tid & 7;
+            const int gi = R0 + 128 * ti + r, gj = R0 + 128 * tj + r;
+            float4 vi = make_float4(0.f, 0.f, 0.f, 0.f), wi = vi, vj = vi, wj = vi;
+            if (gi < n) {
+                vi = __ldcg(reinterpret_cast<const float4*>(jb.Vp + (size_t)gi * NB) + kq);
+                wi = __ldcg(reinterpret_cast<const float4*>(jb.Wp + (size_t)gi * NB) + kq);
+            }
+            if (gj < n) {
+                vj = __ldcg(reinterpret_cast<const float4*>(jb.Vp + (size_t)gj * NB) + kq);
+                wj = __ldcg(reinterpret_cast<const float4*>(jb.Wp + (size_t)gj * NB) + kq);
+            }
+            const float a[4][4] = {{vi.x, vi.y, vi.z, vi.w}, {wi.x, wi.y, wi.z, wi.w},
+                                   {wj.x, wj.y, wj.z, wj.w}, {vj.x, vj.y, vj.z, vj.w}};
+#pragma unroll
+            for (int o = 0; o < 4; ++o)
+#pragma unroll
+                for (int u = 0; u < 4; ++u) sm.op[o][4 * kq + u][r] = (4 * kq + u < kc) ? a[o][u] : 0.f;
+        }
+        __syncthreads();
+        float acc[4][4];
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int b = 0; b < 4; ++b) acc[a][b] = 0.f;
+        for (int k = 0; k < kc; ++k) {
+            const float4 av = *reinterpret_cast<const float4*>(&sm.op[0][k][row4]);
+            const float4 aw = *reinterpret_cast<const float4*>(&sm.op[1][k][row4]);
+            const float4 bw = *reinterpret_cast<const float4*>(&sm.op[2][k][col4]);
+            const float4 bv = *reinterpret_cast<const float4*>(&sm.op[3][k][col4]);
+            const float va[4] = {av.x, av.y, av.z, av.w}, wa[4] = {aw.x, aw.y, aw.z, aw.w};
+            const float wb[4] = {bw.x, bw.y, bw.z, bw.w}, vb[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+#pragma unroll
+                for (int b = 0; b < 4; ++b) acc[a][b] = fmaf(va[a], wb[b], fmaf(wa[a], vb[b], acc[a][b]));
+        }
+        const int gc = R0 + 128 * tj + col4;
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+            const int gi = R0 + 128 * ti + row4 + a;
+            if (gi >= n) continue;
+            float* p = jb.T + (size_t)gi * ldt + gc;
+            if (aligned && gc + 3 < n) {
+                float4 c = __ldcg(reinterpret_cast<const float4*>(p));
+                c.x -= acc[a][0]; c.y -= acc[a][1]; c.z -= acc[a][2]; c.w -= acc[a][3];
+                *reinterpret_cast<float4*>(p) = c;
+            } else {
+#pragma unroll
+                for (int b = 0; b < 4; ++b)
+                    if (gc + b < n) p[b] = __ldcg(p + b) - acc[a][b];
+            }
+        }
+    }
+}
+
+__device__ void run_job(const Job& jb, int rank, Smem& sm) {
+    const int n = jb.n, ldt = jb.ldt, team = jb.team;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    unsigned target = 0;
+    int j0 = 0;
+    if (tid == 0) sm.tau = 0.f;
+    __syncthreads();
+    // optional phase profile (KFACB_TRD_PROF=1): clock64 deltas of thread 0 of the team's first CTA
+    const bool prof_on = jb.prof != nullptr && rank == 0 && tid == 0;
+    long long prof_acc[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    long long t_last = prof_on ? clock64() : 0;
+#define TRD_TICK(slot) do { if (prof_on) { const long long now_ = clock64(); prof_acc[slot] += now_ - t_last; t_last = now_; } } while (0)
+    for (int j = 0; j < n - 1; ++j) {
+        const int jp = j - j0;
+        // ---------------- phase A: finish w_{j-1} (rows >= j), form column j and |x|^2 ----------------
+        if (jp > 0) {
+            reduce_partials(jb, sm, 0, 65);
+            if (warp == 0) finish_prologue(jb, sm, jp - 1, j, true);
+            __syncthreads();
+        }
+        TRD_TICK(0);
+        {
+            const float tau_p = sm.tau, cw = sm.cw;
+            float nrm = 0.f;
+            for (int i = first_own(j, rank, team) + team * warp; i < n; i += team * NWARP) {
+                float vk = lane < jp ? __ldcg(jb.Vp + (size_t)i * NB + lane) : 0.f;
+                float wk = lane < jp - 1 ? __ldcg(jb.Wp + (size_t)i * NB + lane) : 0.f;
+                if (jp > 0) {
+                    const float dot = warp_sum(lane < jp - 1 ? vk * sm.q[lane] + wk * sm.q[32 + lane] : 0.f);
+                    const float yi = __ldcg(jb.y + i);
+                    const float vlast = __shfl_sync(0xffffffffu, vk, jp - 1);
+                    const float wnew = tau_p * (yi - dot) - cw * vlast;
+                    if (lane == jp - 1) { wk = wnew; jb.Wp[(size_t)i * NB + lane] = wnew; }
+                }
+                const float corr = warp_sum(lane < jp ? vk * sm.rowW[lane] + wk * sm.rowV[lane] : 0.f);
+                const float xi = __ldcg(jb.T + (size_t)j * ldt + i) - corr;
+                if (lane == 0) {
+                    if (i == j) jb.d[j] = xi;
+                    else { jb.x[i] = xi; if (i >= j + 2) nrm = fmaf(xi, xi, nrm); }
+                }
+            }
+            if (lane == 0) sm.red[0][warp][0] = nrm;
+            __syncthreads();
+            if (tid == 0) {
+                float tot = 0.f;
+                for (int w = 0; w < NWARP; ++w) tot += sm.red[0][w][0];
+                jb.part[65 * TS + rank] = tot;
+            }
+        }
+        TRD_TICK(1);
+        team_barrier(jb.bar, target, team);
+        TRD_TICK(2);
+        // ---------------- phase B: reflector, y = T v, panel inner products ----------------
+        reduce_partials(jb, sm, 65, 66);
+        if (warp == 0) {
+            const float s2 = sm.q[65];
+            const float alpha = __ldcg(jb.x + j + 1);
+            float beta, tau, scale;
+            if (s2 == 0.f) { tau = 0.f; beta = alpha; scale = 0.f; }
+            else {
+                beta = -copysignf(sqrtf(fmaf(alpha, alpha, s2)), alpha);
+                tau = (beta - alpha) / beta;
+                scale = 1.f / (alpha - beta);
+            }
+            if (lane == 0) {
+                sm.tau = tau; sm.scale = scale;
+                if (rank == 0) { jb.e[j] = beta; jb.tau[j] = tau; }
+            }
+        }
+        __syncthreads();
+        const int c_al = (j + 1) & ~3;
+        {
+            const float scale = sm.scale;
+            for (int c = c_al + tid; c < ldt; c += THREADS) {
+                float val = 0.f;
+                if (c == j + 1) val = 1.f;
+                else if (c > j + 1 && c < n) val = __ldcg(jb.x + c) * scale;
+                sm.v[c] = val;
+            }
+        }
+        __syncthreads();
+        TRD_TICK(3);
+        {
+            float acc_s = 0.f, acc_t = 0.f, acc_vy = 0.f;
+            const int q_beg = c_al >> 2, q_end = ldt >> 2;
+            for (int i = first_own(j + 1, rank, team) + team * warp; i < n; i += team * NWARP) {
+                const float4* row = reinterpret_cast<const float4*>(jb.T + (size_t)i * ldt);
+                float a0 = 0.f, a1 = 0.f;
+                int q = q_beg + lane;
+                for (; q + 96 < q_end; q += 128) {
+                    const float4 m0 = __ldcg(row + q), m1 = __ldcg(row + q + 32), m2 = __ldcg(row + q + 64), m3 = __ldcg(row + q + 96);
+                    const float4 v0 = *reinterpret_cast<const float4*>(&sm.v[4 * q]);
+                    const float4 v1 = *reinterpret_cast<const float4*>(&sm.v[4 * (q + 32)]);
+                    const float4 v2 = *reinterpret_cast<const float4*>(&sm.v[4 * (q + 64)]);
+                    const float4 v3 = *reinterpret_cast<const float4*>(&sm.v[4 * (q + 96)]);
+                    a0 = fmaf(m0.x, v0.x, fmaf(m0.y, v0.y, fmaf(m0.z, v0.z, fmaf(m0.w, v0.w, a0))));
+                    a1 = fmaf(m1.x, v1.x, fmaf(m1.y, v1.y, fmaf(m1.z, v1.z, fmaf(m1.w, v1.w, a1))));
+                    a0 = fmaf(m2.x, v2.x, fmaf(m2.y, v2.y, fmaf(m2.z, v2.z, fmaf(m2.w, v2.w, a0))));
+                    a1 = fmaf(m3.x, v3.x, fmaf(m3.y, v3.y, fmaf(m3.z, v3.z, fmaf(m3.w, v3.w, a1))));
+                }
+                for (; q < q_end; q += 32) {
+                    const float4 m0 = __ldcg(row + q);
+                    const float4 v0 = *reinterpret_cast<const float4*>(&sm.v[4 * q]);
+                    a0 = fmaf(m0.x, v0.x, fmaf(m0.y, v0.y, fmaf(m0.z, v0.z, fmaf(m0.w, v0.w, a0))));
+                }
+                const float yi = warp_sum(a0 + a1);
+                const float vi = sm.v[i];
+                if (lane < jp) {
+                    acc_s = fmaf(__ldcg(jb.Wp + (size_t)i * NB + lane), vi, acc_s);
+                    acc_t = fmaf(__ldcg(jb.Vp + (size_t)i * NB + lane), vi, acc_t);
+                }
+                if (lane == 0) {
+                    jb.y[i] = yi;
+                    acc_vy = fmaf(vi, yi, acc_vy);
+                    jb.Vp[(size_t)i * NB + jp] = vi;
+                    jb.T[(size_t)j * ldt + i] = vi;
+                }
+            }
+            TRD_TICK(4);
+            sm.red[0][warp][lane] = acc_s;
+            sm.red[1][warp][lane] = acc_t;
+            if (lane == 0) sm.red[2][warp][0] = acc_vy;
+            __syncthreads();
+            if (warp == 0) {
+                float s = 0.f, t = 0.f, vy = 0.f;
+                for (int w = 0; w < NWARP; ++w) { s += sm.red[0][w][lane]; t += sm.red[1][w][lane]; vy += sm.red[2][w][0]; }
+                jb.part[lane * TS + rank] = s;
+                jb.part[(32 + lane) * TS + rank] = t;
+                if (lane == 0) jb.part[64 * TS + rank] = vy;
+            }
+        }
+        TRD_TICK(5);
+        team_barrier(jb.bar, target, team);
+        TRD_TICK(6);
+        // ---------------- panel end: finish w_j (rows > j), rank-2k update of the trailing square ----------------
+        if (jp == NB - 1 || j == n - 2) {
+            reduce_partials(jb, sm, 0, 65);
+            if (warp == 0) finish_prologue(jb, sm, jp, 0, false);
+            __syncthreads();
+            const float tau_p = sm.tau, cw = sm.cw;
+            for (int i = first_own(j + 1, rank, team) + team * warp; i < n; i += team * NWARP) {
+                const float vk = lane <= jp ? __ldcg(jb.Vp + (size_t)i * NB + lane) : 0.f;
+                const float wk = lane < jp ? __ldcg(jb.Wp + (size_t)i * NB + lane) : 0.f;
+                const float dot = warp_sum(lane < jp ? vk * sm.q[lane] + wk * sm.q[32 + lane] : 0.f);
+                const float yi = __ldcg(jb.y + i);
+                const float vlast = __shfl_sync(0xffffffffu, vk, jp);
+                if (lane == jp) jb.Wp[(size_t)i * NB + lane] = tau_p * (yi - dot) - cw * vlast;
+            }
+            team_barrier(jb.bar, target, team);
+            TRD_TICK(7);
+            rank2k_update(jb, sm, j + 1, jp + 1, rank);
+            team_barrier(jb.bar, target, team);
+            TRD_TICK(8);
+            j0 = j + 1;
+        }
+    }
+    if (rank == 0 && tid == 0) jb.d[n - 1] = __ldcg(jb.T + (size_t)(n - 1) * ldt + (n - 1));
+    if (prof_on)
+        for (int q = 0; q < 9; ++q) jb.prof[q] = prof_acc[q];
+#undef TRD_TICK
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(THREADS, 1)
+trd_kernel(const Job* jobs, const int* cta_begin, const int* entries) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
+    __shared__ Job jb;
+    for (int e = cta_begin[blockIdx.x]; e < cta_begin[blockIdx.x + 1]; ++e) {
+        __syncthreads();
+        if (threadIdx.x == 0) jb = jobs[entries[2 * e]];
+        __syncthreads();
+        run_job(jb, entries[2 * e + 1], sm);
+    }
+}
+
+// lower triangle of src mirrored into the n x ldt work array (the reference's eigh reads the lower triangle only).
+// grid (row tiles of the largest matrix, jobs); a block walks the tiles (ti, 0..ti) of its row of 32x32 tiles.
+__global__ void trd_copy_kernel(const Job* jobs, const float* const* src) {
+    __shared__ float tile[32][33];
+    const Job jb = jobs[blockIdx.y];
+    const int n = jb.n, ldt = jb.ldt;
+    const int nt = (n + 31) >> 5;
+    const int ti = blockIdx.x;
+    if (ti >= nt) return;
+    const float* A = src[blockIdx.y];
+    const int lx = threadIdx.x & 31, ly = threadIdx.x >> 5;          // 256 threads
+    for (int tj = 0; tj <= ti; ++tj) {
+        __syncthreads();
+        for (int r = ly; r < 32; r += 8) {
+            const int gi = 32 * ti + r, gc = 32 * tj + lx;
+            tile[r][lx] = (gi < n && gc < n) ? A[(size_t)gi * n + gc] : 0.f;
+        }
+        __syncthreads();
+        for (int r = ly; r < 32; r += 8) {
+            const int gi = 32 * ti + r, gc = 32 * tj + lx;
+            if (gi < n && gc < ldt) {                                    // (pad columns [n, ldt) get zeros)
+                float v = tile[r][lx];
+                if (ti == tj && lx > r) v = tile[lx][r];
+                jb.T[(size_t)gi * ldt + gc] = gc < n ? v : 0.f;
+            }
+            if (ti != tj) {
+                const int ui = 32 * tj + r, uc = 32 * ti + lx;           // mirrored tile
+                if (ui < n && uc < ldt) jb.T[(size_t)ui * ldt + uc] = uc < n ? tile[lx][r] : 0.f;
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// host: team sizes and the per-CTA schedule
+// ---------------------------------------------------------------------------
+static double job_time(int n, int team) {
+    const double t_step = team > 1 ? 3.0e-6 : 1.5e-6;                 // two barriers + the short phases
+    double bw = 40e9 * team;                                          // streaming rate of a team (HBM share / SM)
+    if (bw > 5.2e12) bw = 5.2e12;
+    const double n3 = (double)n * n * n;
+    // product: 4 m^2 bytes per column = 4/3 n^3 bytes; rank-2k updates: 4/3 n^3 flops at ~0.2 TFLOP/s per SM (SIMT)
+    return n * t_step + (4.0 / 3.0) * n3 / bw + (4.0 / 3.0) * n3 / (0.2e12 * team);
+}
+
+int plan_teams(const int* n, int njobs, int sms, int* team, int* cta_begin, int* entries) {
+    static int forced = -2;                                           // KFACB_TRD_TEAM=k: every job on a team of k (tuning aid)
+    if (forced == -2) { const char* e = getenv("KFACB_TRD_TEAM"); forced = (e && *e) ? atoi(e) : -1; }
+    static const int cand[] = {1, 2, 3, 4, 6, 8, 12, 16, 24, 32, 48, 64, 96, 128, 1 << 30};
+    struct TeamRec { int size; double load; int first_job, njobs; };
+    int* order = new int[njobs];
+    for (int i = 0; i < njobs; ++i) order[i] = i;
+    for (int a = 1; a < njobs; ++a) {                                 // by n descending (stable)
+        const int v = order[a];
+        int b = a - 1;
+        while (b >= 0 && n[order[b]] < n[v]) { order[b + 1] = order[b]; --b; }
+        order[b + 1] = v;
+    }
+    int* t_of = new int[njobs];
+    int* team_of_job = new int[njobs];
+    TeamRec* teams = new TeamRec[njobs > 0 ? njobs : 1];
+    int nteams = 0;
+    auto try_pack = [&](double limit) -> bool {
+        nteams = 0;
+        int used = 0;
+        for (int a = 0; a < njobs; ++a) {
+            const int jn = n[order[a]];
+            int tsel = -1;
+            if (forced > 0) tsel = forced > sms ? sms : forced;
+            else for (int c : cand) {
+                const int t = c > sms ? sms : c;
+                if (job_time(jn, t) <= limit) { tsel = t; break; }
+                if (t == sms) break;
+            }
+            if (tsel < 0) return false;
+            const double jt = job_time(jn, tsel);
+            int k = -1;
+            for (int q = 0; q < nteams; ++q)
+                if (teams[q].size == tsel && teams[q].load + jt <= limit) { k = q; break; }
+            if (k < 0) {
+                if (used + tsel > sms) return false;
+                k = nteams++;
+                teams[k] = TeamRec{tsel, 0.0, 0, 0};
+                used += tsel;
+            }
+            teams[k].load += jt;
+            t_of[a] = tsel;
+            team_of_job[a] = k;
+        }
+        return true;
+    };
+    double lo = 0.0, hi = 0.0;
+    for (int i = 0; i < njobs; ++i) { hi += job_time(n[i], 1); const double t = job_time(n[i], sms); if (t > lo) lo = t; }
+    if (hi < lo) hi = lo;
+    while (!try_pack(hi)) hi *= 2.0;
+    for (int it = 0; it < 40; ++it) {
+        const double mid = 0.5 * (lo + hi);
+        if (try_pack(mid)) hi = mid; else lo = mid;
+    }
+    try_pack(hi);
+    // lay the teams out on consecutive CTAs; CTA c of team k runs the team's jobs in order
+    int* team_base = new int[nteams > 0 ? nteams : 1];
+    int used = 0;
+    for (int k = 0; k < nteams; ++k) { team_base[k] = used; used += teams[k].size; }
+    int ne = 0;
+    for (int c = 0; c <= sms; ++c) cta_begin[c] = 0;
+    for (int k = 0; k < nteams; ++k)
+        for (int r = 0; r < teams[k].size; ++r) {
+            const int c = team_base[k] + r;
+            cta_begin[c] = ne;
+            for (int a = 0; a < njobs; ++a)
+                if (team_of_job[a] == k) { entries[2 * ne] = order[a]; entries[2 * ne + 1] = r; ++ne; }
+        }
+    for (int c = used; c <= sms; ++c) cta_begin[c] = ne;
+    for (int a = 0; a < njobs; ++a) team[order[a]] = t_of[a];
+    delete[] order; delete[] t_of; delete[] team_of_job; delete[] teams; delete[] team_base;
+    return used > 0 ? used : 0;        // CTAs in use (the grid); entries written: sum over CTAs
+}
+
+cudaError_t launch(const Job* d_jobs, const int* d_cta_begin, const int* d_entries, int grid, cudaStream_t st) {
+    if (grid <= 0) return cudaSuccess;
+    cudaError_t e = cudaFuncSetAttribute(trd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem));
+    if (e != cudaSuccess) return e;
+    void* args[] = {(void*)&d_jobs, (void*)&d_cta_begin, (void*)&d_entries};
+    e = cudaLaunchCooperativeKernel((const void*)trd_kernel, dim3(grid), dim3(THREADS), args, sizeof(Smem), st);
+    count_launch();
+    return e;
+}
+
+cudaError_t launch_copy(const Job* d_jobs, const float* const* d_src, int njobs, int nmax, cudaStream_t st) {
+    if (njobs <= 0) return cudaSuccess;
+    trd_copy_kernel<<<dim3((nmax + 31) / 32, njobs), 256, 0, st>>>(d_jobs, d_src);
+    count_launch();
+    return cudaGetLastError();
+}
+
+}  // namespace trd
+}  // namespace kfacb

@@ -1,0 +1,56 @@
+// eigh_trd.cuh -- interface between the pieces of the tridiagonalisation + divide-and-conquer eigensolver
+// (eigh_trd.cu: Householder tridiagonalisation, eigh_dc.cu: D&C on the tridiagonal matrix, back-transformation
+// and the driver that kfacb_eigh_batched dispatches to).
+#pragma once
+#include "common.cuh"
+
+namespace kfacb {
+namespace trd {
+
+constexpr int NB = 32;            // panel width = warp size: lane k owns panel column k
+constexpr int THREADS = 1024;
+constexpr int NWARP = THREADS / 32;
+constexpr int MAXN = 8192;        // the reflector vector of one column lives in shared memory
+constexpr int NPART = 66;         // partial sums per team member: [0,32) W^T v, [32,64) V^T v, [64] v.y, [65] |x|^2
+constexpr int TS = 160;           // slots per quantity (>= largest team): part[k * TS + rank]
+
+// one matrix to tridiagonalise: T (n x ldt, symmetric copy of the input) -> d, e, tau; reflector j is left in
+// T[j][j+1 .. n) (v_j[0] = 1 stored explicitly)
+struct Job {
+    float* T;
+    float* d;
+    float* e;
+    float* tau;
+    float* Vp;            // n x NB panel of reflectors
+    float* Wp;            // n x NB panel of W
+    float* x;             // n: column being reduced
+    float* y;             // n: T v
+    float* part;          // NPART x TS partial sums
+    unsigned* bar;        // team barrier counter (zero on entry)
+    long long* prof;      // NULL, or 9 clock64 totals of the phases (debug: KFACB_TRD_PROF=1)
+    int n, ldt, team;
+};
+
+struct Sched {            // host-built: CTA c runs entries [begin[c], begin[c+1]) of (job, rank)
+    int grid;             // CTAs to launch
+};
+
+// Chooses a team size per job and packs the teams on `sms` CTAs (moldable-task list scheduling on a simple
+// latency + bandwidth cost model).  Outputs, per job, team[j]; and the per-CTA schedule as flat arrays
+// (cta_begin: sms + 1 ints; entries: 2 ints (job, rank) each).  Returns the number of entries.
+int plan_teams(const int* n, int njobs, int sms, int* team, int* cta_begin, int* entries);
+
+// launches the persistent kernel (cooperative launch: all CTAs co-resident)
+cudaError_t launch(const Job* d_jobs, const int* d_cta_begin, const int* d_entries, int grid, cudaStream_t st);
+
+// symmetrised copy (lower triangle mirrored) of the inputs into the work arrays; src[j] n x n, dst = jobs[j].T
+cudaError_t launch_copy(const Job* d_jobs, const float* const* d_src, int njobs, int nmax, cudaStream_t st);
+
+}  // namespace trd
+
+// driver of the whole n > 128 path (eigh_dc.cu)
+size_t eigh_tdc_workspace_bytes(const int32_t* n, int count, const int* idx, int nb);
+int eigh_tdc_run(const int32_t* n, const int* idx, int nb, const float* const* M, float* const* Q, float* const* d,
+                 float eps_floor, int32_t* sweeps_out, char* ws, size_t ws_bytes, cudaStream_t st);
+
+}  // namespace kfacb
