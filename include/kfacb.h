@@ -18,7 +18,8 @@
  *  - the library never allocates or frees device memory: the caller owns all
  *    buffers, including workspaces whose sizes come from the *_workspace_bytes
  *    queries.  Workspaces must be 256-byte aligned.
- *  - all work is enqueued on `stream`; no call synchronises the device.
+ *  - all work is enqueued on `stream`; no call synchronises the device or the host
+ *    (exceptions, both opt-in debug paths: KFACB_EIGH_ALGO=jacobi, KFACB_TRD_PROF=1).
  *  - host arrays (descriptors, pointer tables) are read before the call
  *    returns and may be reused immediately.
  *  - all matrices are dense row-major fp32.
@@ -111,12 +112,20 @@ int    kfacb_factor_update(const kfacb_layer_t* layers, int32_t count,
  * kfac/kfac_preconditioner_eigen_dp.py:62-75 (and the unused cuSOLVER wrapper
  * packages/tcmm/src/tcmm_kernel.cu:56-116).
  *
- * For each i: M[i] (n[i] x n[i], symmetric, read only) = Q diag(d) Q^T with d
- * ascending, eigenvectors in the COLUMNS of Q[i] (row-major n x n), then
- * d <- d * (d > eps_floor).  Jacobi based (one CTA per matrix in shared memory
- * for n <= 128, implicit two-sided block Jacobi above); eigenvectors are defined up
- * to sign / rotation inside degenerate clusters.
- * sweeps_out (device int32[count], may be NULL) receives the number of sweeps.
+ * For each i: M[i] (n[i] x n[i], symmetric -- the lower triangle is read, like
+ * torch.linalg.eigh) = Q diag(d) Q^T with d ascending, eigenvectors in the COLUMNS
+ * of Q[i] (row-major n x n), then d <- d * (d > eps_floor).  Eigenvectors are
+ * defined up to sign / rotation inside degenerate clusters.
+ *   n <= 128: two-sided cyclic Jacobi, one CTA per matrix, in shared memory.
+ *   n  > 128: Householder tridiagonalisation of the whole batch in ONE persistent
+ *             kernel (teams of CTAs per matrix), divide and conquer on the
+ *             tridiagonal matrices, block-reflector back-transformation on the
+ *             tensor cores.  Fixed launch sequence: the call only ENQUEUES work (no
+ *             convergence test, no host synchronisation, CUDA-graph capturable).
+ *             n <= 8192.  (KFACB_EIGH_ALGO=jacobi selects the round-1 block-Jacobi
+ *             path, which does synchronise the host on its progress events.)
+ * sweeps_out (device int32[count], may be NULL) receives the number of Jacobi
+ * sweeps (n <= 128) or 1.
  * ------------------------------------------------------------------------- */
 size_t kfacb_eigh_workspace_bytes(const int32_t* n, int32_t count);
 int    kfacb_eigh_batched(const int32_t* n, int32_t count,
@@ -125,12 +134,17 @@ int    kfacb_eigh_batched(const int32_t* n, int32_t count,
                           void* workspace, size_t workspace_bytes,
                           kfacb_stream_t stream);
 
-/* Benchmark aid.  With the environment variable KFACB_PROFILE=1, kfacb_eigh_batched times its three
- * per-round kernels with CUDA events (synchronising every round: never use it inside a timed region) and
- * this call returns the totals of the last such run:
- *   out8 = { rounds, ms projected-block kernel, ms solve kernel, ms update kernel,
- *            algorithmic HBM bytes of the projected-block launches (8 n_pad^2 per active matrix and round),
- *            algorithmic HBM bytes of the update launches (16 n_pad^2 ...), matrices, block pairs } */
+/* Scheduler introspection (no GPU needed): team_out[i] = CTAs that tridiagonalise matrix i on a device with
+ * `sms` SMs (0 for n[i] <= 128); returns the number of CTAs of the persistent kernel, < 0 on bad arguments. */
+int    kfacb_eigh_plan_teams(const int32_t* n, int32_t count, int32_t sms, int32_t* team_out);
+
+/* Benchmark aid.  kfacb_eigh_batched records CUDA events on the caller's stream around its stages (asynchronous);
+ * this call waits for the last one and returns, for the LAST call on the current device:
+ *   out8 = { ms tridiagonalisation, ms divide and conquer, ms back-transformation + write,
+ *            algorithmic bytes of the tridiagonalisation (sum 4/3 n^3: one read of the trailing matrix per column),
+ *            sum n^3 of the n > 128 matrices, their count, CTAs of the persistent kernel, 0 }
+ * (With KFACB_EIGH_ALGO=jacobi and KFACB_PROFILE=1: the per-round kernel totals of the block-Jacobi path,
+ *  { rounds, ms projected-block, ms solve, ms update, bytes H, bytes update, matrices, block pairs }.) */
 int    kfacb_eigh_last_profile(double* out8);
 
 /* ---------------------------------------------------------------------------
@@ -178,6 +192,59 @@ int    kfacb_precond_inverse(const kfacb_layer_t* layers, int32_t count,
                              float* const* out,
                              void* workspace, size_t workspace_bytes,
                              kfacb_stream_t stream);
+
+/* Same as kfacb_precond_eigen / _inverse, but the epilogue of the LAST GEMM also stores every output element at
+ * byte offset peer_deltas[q] from its local address, for q < npeers: with the deltas of an attached exchange
+ * (kfacb_exchange_peer_deltas) the preconditioned gradient lands in every peer's slab over NVLink while it is
+ * being produced -- the exchange of kfac_preconditioner_inv.py:164-175 fused into the producing kernel.
+ * `out[i]` must point into the local exchange slab.  Bracket with kfacb_exchange_begin / _signal. */
+int    kfacb_precond_eigen_bcast(const kfacb_layer_t* layers, int32_t count,
+                                 const float* const* QA, const float* const* QG,
+                                 const float* const* dA, const float* const* dG,
+                                 const float* const* wgrad, const float* const* bgrad,
+                                 float* const* out, float damping,
+                                 int32_t npeers, const int64_t* peer_deltas,
+                                 void* workspace, size_t workspace_bytes,
+                                 kfacb_stream_t stream);
+int    kfacb_precond_inverse_bcast(const kfacb_layer_t* layers, int32_t count,
+                                   const float* const* invA, const float* const* invG,
+                                   const float* const* wgrad, const float* const* bgrad,
+                                   float* const* out,
+                                   int32_t npeers, const int64_t* peer_deltas,
+                                   void* workspace, size_t workspace_bytes,
+                                   kfacb_stream_t stream);
+
+/* ---------------------------------------------------------------------------
+ * (3b) Exchange of the preconditioned gradients between the ranks of ONE node.
+ * Replaces `_communicate_pred`, kfac/kfac_preconditioner_inv.py:164-175 (one hvd/torch broadcast per layer).
+ *
+ * Every rank creates an exchange with the same slab size; the slab (device memory OWNED BY THE EXCHANGE -- the one
+ * exception to "the library never allocates": it has to be IPC-exportable) holds all layers' preconditioned
+ * gradients.  The 128-byte handles are all-gathered by the caller (any host transport) and connected: the slabs
+ * are then mapped into each other (CUDA IPC, peer memory over NVLink / NVSwitch).  Per step, on the caller's
+ * stream, in this order on every rank (all calls only enqueue tiny kernels):
+ *     kfacb_exchange_begin     wait until every peer has released the previous step's slab
+ *     ... produce the owned segment: kfacb_precond_*_bcast (fused: stored into every peer while computed), or
+ *         plain kfacb_precond_* followed by kfacb_exchange_push(offset, bytes) (one copy kernel, then signals) ...
+ *     kfacb_exchange_signal    (fused variant only) tell every peer that this rank's segment has landed
+ *     kfacb_exchange_wait      wait until every peer's segment has landed in the local slab
+ *     ... consume the whole slab (kfacb_finalize_grads) ...
+ *     kfacb_exchange_release   tell every peer that the local slab may be overwritten
+ * A rank that owns no layer still calls begin / signal (or push with 0 bytes) / wait / release.
+ * ------------------------------------------------------------------------- */
+typedef struct kfacb_exchange kfacb_exchange_t;
+#define KFACB_EXCHANGE_HANDLE_BYTES 128
+int    kfacb_exchange_create(int32_t rank, int32_t size, size_t slab_bytes, kfacb_exchange_t** out);
+int    kfacb_exchange_handle(kfacb_exchange_t* ex, void* handle_out /* KFACB_EXCHANGE_HANDLE_BYTES */);
+int    kfacb_exchange_connect(kfacb_exchange_t* ex, const void* all_handles /* size x KFACB_EXCHANGE_HANDLE_BYTES, by rank */);
+void*  kfacb_exchange_slab(kfacb_exchange_t* ex);
+int    kfacb_exchange_peer_deltas(kfacb_exchange_t* ex, int64_t* deltas_out /* size - 1 */, int32_t* npeers_out);
+int    kfacb_exchange_begin(kfacb_exchange_t* ex, kfacb_stream_t stream);
+int    kfacb_exchange_signal(kfacb_exchange_t* ex, kfacb_stream_t stream);
+int    kfacb_exchange_push(kfacb_exchange_t* ex, size_t offset_bytes, size_t nbytes, kfacb_stream_t stream);
+int    kfacb_exchange_wait(kfacb_exchange_t* ex, kfacb_stream_t stream);
+int    kfacb_exchange_release(kfacb_exchange_t* ex, kfacb_stream_t stream);
+int    kfacb_exchange_destroy(kfacb_exchange_t* ex);
 
 /* ---------------------------------------------------------------------------
  * (4) KL-clip and in-place gradient rewrite.  Replaces

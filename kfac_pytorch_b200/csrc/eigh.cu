@@ -1080,12 +1080,6 @@ static cudaError_t launch_solve(GroupRun& gr, const GroupPlan& gp, int round, in
 
 using namespace kfacb;
 
-extern "C" int kfacb_eigh_last_profile(double* out8) {
-    if (!out8) return KFACB_ERR_ARG;
-    for (int i = 0; i < 8; ++i) out8[i] = g_profile[i];
-    return KFACB_OK;
-}
-
 // n > 128: tridiagonalisation + divide and conquer (eigh_trd.cu / eigh_dc.cu) unless KFACB_EIGH_ALGO=jacobi asks
 // for the round-1 block-Jacobi path below (kept for A/B comparisons)
 static bool use_block_jacobi() {
@@ -1093,6 +1087,13 @@ static bool use_block_jacobi() {
     if (v < 0) { const char* e = getenv("KFACB_EIGH_ALGO"); v = (e && (e[0] == 'j' || e[0] == 'J')) ? 1 : 0; }
     return v == 1;
 }
+extern "C" int kfacb_eigh_last_profile(double* out8) {
+    if (!out8) return KFACB_ERR_ARG;
+    if (!use_block_jacobi()) return eigh_tdc_last_profile(out8);
+    for (int i = 0; i < 8; ++i) out8[i] = g_profile[i];
+    return KFACB_OK;
+}
+
 static size_t direct_tables_bytes(int n_direct) {
     return align_up(sizeof(DirectMat) * (size_t)(n_direct + 1), 256) + align_up(sizeof(int) * (size_t)(n_direct + 1), 256);
 }

@@ -830,6 +830,54 @@ static void build_plan(const int32_t* n, const int* idx, int nb, Plan& pl) {
 
 using namespace dc;
 
+// CUDA events around the stages of the last call (per device): recorded on the caller's stream (asynchronous, no
+// host synchronisation), read by kfacb_eigh_last_profile after the caller has synchronised
+struct StageEvents { cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr}; bool ok = false; double bytes_trd = 0, n3 = 0; int nb = 0, grid = 0; };
+static StageEvents g_stage[64];
+static StageEvents* stage_events() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+    StageEvents& s = g_stage[dev];
+    if (!s.ok) {
+        for (int i = 0; i < 4; ++i) if (cudaEventCreate(&s.ev[i]) != cudaSuccess) return nullptr;
+        s.ok = true;
+    }
+    return &s;
+}
+int eigh_tdc_last_profile(double* out8) {
+    StageEvents* s = stage_events();
+    for (int i = 0; i < 8; ++i) out8[i] = 0.0;
+    if (!s || s->nb == 0) return KFACB_OK;
+    if (cudaEventSynchronize(s->ev[3]) != cudaSuccess) { (void)cudaGetLastError(); return KFACB_OK; }
+    float t = 0.f;
+    if (cudaEventElapsedTime(&t, s->ev[0], s->ev[1]) == cudaSuccess) out8[0] = t;      // tridiagonalisation (copy + persistent kernel)
+    if (cudaEventElapsedTime(&t, s->ev[1], s->ev[2]) == cudaSuccess) out8[1] = t;      // divide and conquer
+    if (cudaEventElapsedTime(&t, s->ev[2], s->ev[3]) == cudaSuccess) out8[2] = t;      // back-transformation + write
+    out8[3] = s->bytes_trd;     // algorithmic bytes of the tridiagonalisation: sum 4/3 n^3 (one read of the trailing matrix per column)
+    out8[4] = s->n3;            // sum n^3 of the blocked matrices
+    out8[5] = s->nb; out8[6] = s->grid;
+    (void)cudaGetLastError();
+    return KFACB_OK;
+}
+
+}  // namespace kfacb
+
+// Introspection of the scheduler (tests): team size per matrix (0 for the n <= 128 matrices that
+// take the direct path) for a device with `sms` SMs; returns the number of CTAs of the persistent kernel.
+extern "C" int kfacb_eigh_plan_teams(const int32_t* n, int32_t count, int32_t sms, int32_t* team_out) {
+    if (!n || !team_out || count < 0 || sms <= 0) return -1;
+    std::vector<int> ns, idx, team, cta(sms + 1, 0);
+    for (int i = 0; i < count; ++i) { team_out[i] = 0; if (n[i] > kfacb::DIRECT_MAX_N) { ns.push_back(n[i]); idx.push_back(i); } }
+    if (ns.empty()) return 0;
+    team.assign(ns.size(), 1);
+    std::vector<int> entries((size_t)2 * ns.size() * sms + 2, 0);
+    const int grid = kfacb::trd::plan_teams(ns.data(), (int)ns.size(), sms, team.data(), cta.data(), entries.data());
+    for (size_t a = 0; a < ns.size(); ++a) team_out[idx[a]] = team[a];
+    return grid;
+}
+
+namespace kfacb {
+
 size_t eigh_tdc_workspace_bytes(const int32_t* n, int count, const int* idx, int nb) {
     (void)count;
     if (nb <= 0) return 0;
@@ -908,10 +956,17 @@ int eigh_tdc_run(const int32_t* n, const int* idx, int nb, const float* const* M
     const bool tc = use_tc_gemm();
     static int dbg = -1;                        // KFACB_TDC_DEBUG=1: skip the back-transformation (Q = eigenvectors of T)
     if (dbg < 0) { const char* e = getenv("KFACB_TDC_DEBUG"); dbg = (e && *e) ? atoi(e) : 0; }
+    StageEvents* sev = stage_events();
+    if (sev) {
+        sev->nb = nb; sev->grid = pl.grid; sev->bytes_trd = 0; sev->n3 = 0;
+        for (int a = 0; a < nb; ++a) { const double n3 = (double)pl.ml[a].n * pl.ml[a].n * pl.ml[a].n; sev->n3 += n3; sev->bytes_trd += 4.0 / 3.0 * n3; }
+        cudaEventRecord(sev->ev[0], st);
+    }
     // ---- (1) tridiagonalisation ----
     KFACB_CHECK_CUDA(trd::launch_copy(d_jobs, reinterpret_cast<const float* const*>(tb + pl.t_src), nb, pl.nmax, st));
     KFACB_CHECK_CUDA(trd::launch(d_jobs, reinterpret_cast<const int*>(tb + pl.t_cta),
                                  reinterpret_cast<const int*>(tb + pl.t_ent), pl.grid, st));
+    if (sev) cudaEventRecord(sev->ev[1], st);
     if (trd_prof) {
         std::vector<long long> hp((size_t)16 * nb);
         if (cudaStreamSynchronize(st) == cudaSuccess &&
@@ -969,6 +1024,7 @@ int eigh_tdc_run(const int32_t* n, const int* idx, int nb, const float* const* M
         count_launch(8);
         KFACB_CHECK_LAUNCH();
     }
+    if (sev) cudaEventRecord(sev->ev[2], st);
     // ---- (3) back-transformation ----
     if (dbg != 1) {
         const int np = (int)pl.panel_tiles.size();
@@ -996,6 +1052,7 @@ int eigh_tdc_run(const int32_t* n, const int* idx, int nb, const float* const* M
     eig_write_kernel<<<dim3(cdiv(pl.nmax, 32), cdiv(pl.nmax, 32), nb), 256, 0, st>>>(
         d_mats, eps_floor, sweeps_out, reinterpret_cast<const int*>(tb + pl.t_oidx));
     KFACB_CHECK_LAUNCH();
+    if (sev) cudaEventRecord(sev->ev[3], st);
     return KFACB_OK;
 }
 

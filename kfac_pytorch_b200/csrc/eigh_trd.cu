@@ -43,13 +43,13 @@ __device__ __forceinline__ void team_barrier(unsigned* ctr, unsigned& target, in
     if (team > 1) {
         target += (unsigned)team;
         if (threadIdx.x == 0) {
-            __threadfence();
-            asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(ctr) : "memory");
+            __threadfence();                                     // the CTA's writes (ordered by the barrier above) before the arrival
+            asm volatile("red.relaxed.gpu.global.add.u32 [%0], 1;" ::"l"(ctr) : "memory");
             unsigned v;
             do {
-                asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
+                asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
             } while (v < target);
-            __threadfence();
+            __threadfence();                                     // acquire side (also drops stale L1 lines)
         }
         __syncthreads();
     }
@@ -61,15 +61,27 @@ __device__ __forceinline__ int first_own(int r0, int rank, int team) {
     return r0 + o;
 }
 
-// Team-wide sums of the partials [kbeg, kend): quantity k lives in part[k * TS + rank]; a warp adds the team's
-// slots of one quantity (coalesced, fixed order: identical bits on every CTA).  All threads; ends with a barrier.
-__device__ __forceinline__ void reduce_partials(const Job& jb, Smem& sm, int kbeg, int kend) {
+// Team-wide sums of the partial sums of the last product pass: quantity k lives in part[k * TS + rank]; one warp
+// adds the team's slots of a quantity (coalesced, fixed order: identical bits on every CTA).  Only the kc live panel
+// columns of s = W^T v and t = V^T v are read.  The loads of a warp's quantities are issued together.
+// All threads; ends with a barrier.
+__device__ __forceinline__ void reduce_st(const Job& jb, Smem& sm, int kc) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int k = kbeg + warp; k < kend; k += NWARP) {
-        float a = 0.f;
-        for (int r = lane; r < jb.team; r += 32) a += __ldcg(jb.part + k * TS + r);
-        a = warp_sum(a);
-        if (lane == 0) sm.q[k] = a;
+    constexpr int PER = (65 + NWARP - 1) / NWARP;               // quantities per warp
+    float a[PER];
+#pragma unroll
+    for (int u = 0; u < PER; ++u) {
+        const int k = warp + NWARP * u;
+        a[u] = 0.f;
+        const bool live = k < 65 && (k == 64 || (k & 31) < kc);
+        if (live)
+            for (int r = lane; r < jb.team; r += 32) a[u] += __ldcg(jb.part + k * TS + r);
+    }
+#pragma unroll
+    for (int u = 0; u < PER; ++u) {
+        const int k = warp + NWARP * u;
+        const float t = warp_sum(a[u]);
+        if (lane == 0 && k < 65) sm.q[k] = t;
     }
     __syncthreads();
 }
@@ -97,21 +109,25 @@ __device__ __forceinline__ void finish_prologue(const Job& jb, Smem& sm, int kc,
     }
 }
 
-// A[R0.., R0..] -= V W^T + W V^T over the first kc panel columns; tiles of 128x128 dealt to the team
+// A[R0.., R0..] -= V W^T + W V^T over the first kc panel columns; tiles of 128x128 dealt to the team.
+// 16 warps = 4 x 4, lanes = 4 (row groups of 8) x 8 (column groups of 4): 8x4 outputs per thread; per k a warp
+// reads 6 shared-memory wavefronts (broadcast within a group) for 64 FMAs -> FMA bound.
 __device__ void rank2k_update(const Job& jb, Smem& sm, int R0, int kc, int rank) {
     const int n = jb.n, ldt = jb.ldt;
     const int mt = n - R0;
     if (mt <= 0) return;
     const int nt = (mt + 127) >> 7;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int row4 = 16 * (warp >> 2) + 4 * (lane >> 3);         // 8 x 4 warps, lanes 4 (rows) x 8 (cols)
+    const int row8 = 32 * (warp >> 2) + 8 * (lane >> 3);
     const int col4 = 32 * (warp & 3) + 4 * (lane & 7);
     const bool aligned = (R0 & 3) == 0;
     for (int q = rank; q < nt * nt; q += jb.team) {
         const int ti = q / nt, tj = q - ti * nt;
         __syncthreads();
-        {
-            const int r = tid >> 3, kq = tid & 7;
+#pragma unroll
+        for (int it = 0; it < (128 * 8) / THREADS; ++it) {
+            const int item = tid + it * THREADS;
+            const int r = item >> 3, kq = item & 7;
             const int gi = R0 + 128 * ti + r, gj = R0 + 128 * tj + r;
             float4 vi = make_float4(0.f, 0.f, 0.f, 0.f), wi = vi, vj = vi, wj = vi;
             if (gi < n) {
@@ -130,27 +146,30 @@ __device__ void rank2k_update(const Job& jb, Smem& sm, int R0, int kc, int rank)
                 for (int u = 0; u < 4; ++u) sm.op[o][4 * kq + u][r] = (4 * kq + u < kc) ? a[o][u] : 0.f;
         }
         __syncthreads();
-        float acc[4][4];
+        float acc[8][4];
 #pragma unroll
-        for (int a = 0; a < 4; ++a)
+        for (int a = 0; a < 8; ++a)
 #pragma unroll
             for (int b = 0; b < 4; ++b) acc[a][b] = 0.f;
         for (int k = 0; k < kc; ++k) {
-            const float4 av = *reinterpret_cast<const float4*>(&sm.op[0][k][row4]);
-            const float4 aw = *reinterpret_cast<const float4*>(&sm.op[1][k][row4]);
+            const float4 av0 = *reinterpret_cast<const float4*>(&sm.op[0][k][row8]);
+            const float4 av1 = *reinterpret_cast<const float4*>(&sm.op[0][k][row8 + 4]);
+            const float4 aw0 = *reinterpret_cast<const float4*>(&sm.op[1][k][row8]);
+            const float4 aw1 = *reinterpret_cast<const float4*>(&sm.op[1][k][row8 + 4]);
             const float4 bw = *reinterpret_cast<const float4*>(&sm.op[2][k][col4]);
             const float4 bv = *reinterpret_cast<const float4*>(&sm.op[3][k][col4]);
-            const float va[4] = {av.x, av.y, av.z, av.w}, wa[4] = {aw.x, aw.y, aw.z, aw.w};
+            const float va[8] = {av0.x, av0.y, av0.z, av0.w, av1.x, av1.y, av1.z, av1.w};
+            const float wa[8] = {aw0.x, aw0.y, aw0.z, aw0.w, aw1.x, aw1.y, aw1.z, aw1.w};
             const float wb[4] = {bw.x, bw.y, bw.z, bw.w}, vb[4] = {bv.x, bv.y, bv.z, bv.w};
 #pragma unroll
-            for (int a = 0; a < 4; ++a)
+            for (int a = 0; a < 8; ++a)
 #pragma unroll
                 for (int b = 0; b < 4; ++b) acc[a][b] = fmaf(va[a], wb[b], fmaf(wa[a], vb[b], acc[a][b]));
         }
         const int gc = R0 + 128 * tj + col4;
 #pragma unroll
-        for (int a = 0; a < 4; ++a) {
-            const int gi = R0 + 128 * ti + row4 + a;
+        for (int a = 0; a < 8; ++a) {
+            const int gi = R0 + 128 * ti + row8 + a;
             if (gi >= n) continue;
             float* p = jb.T + (size_t)gi * ldt + gc;
             if (aligned && gc + 3 < n) {
@@ -182,7 +201,7 @@ __device__ void run_job(const Job& jb, int rank, Smem& sm) {
         const int jp = j - j0;
         // ---------------- phase A: finish w_{j-1} (rows >= j), form column j and |x|^2 ----------------
         if (jp > 0) {
-            reduce_partials(jb, sm, 0, 65);
+            reduce_st(jb, sm, jp - 1);
             if (warp == 0) finish_prologue(jb, sm, jp - 1, j, true);
             __syncthreads();
         }
@@ -191,17 +210,18 @@ __device__ void run_job(const Job& jb, int rank, Smem& sm) {
             const float tau_p = sm.tau, cw = sm.cw;
             float nrm = 0.f;
             for (int i = first_own(j, rank, team) + team * warp; i < n; i += team * NWARP) {
-                float vk = lane < jp ? __ldcg(jb.Vp + (size_t)i * NB + lane) : 0.f;
+                float vk = lane < jp ? __ldcg(jb.Vp + (size_t)i * NB + lane) : 0.f;       // (all four loads in flight together)
                 float wk = lane < jp - 1 ? __ldcg(jb.Wp + (size_t)i * NB + lane) : 0.f;
+                const float yi = jp > 0 ? __ldcg(jb.y + i) : 0.f;
+                const float tji = __ldcg(jb.T + (size_t)j * ldt + i);
                 if (jp > 0) {
                     const float dot = warp_sum(lane < jp - 1 ? vk * sm.q[lane] + wk * sm.q[32 + lane] : 0.f);
-                    const float yi = __ldcg(jb.y + i);
                     const float vlast = __shfl_sync(0xffffffffu, vk, jp - 1);
                     const float wnew = tau_p * (yi - dot) - cw * vlast;
                     if (lane == jp - 1) { wk = wnew; jb.Wp[(size_t)i * NB + lane] = wnew; }
                 }
                 const float corr = warp_sum(lane < jp ? vk * sm.rowW[lane] + wk * sm.rowV[lane] : 0.f);
-                const float xi = __ldcg(jb.T + (size_t)j * ldt + i) - corr;
+                const float xi = tji - corr;
                 if (lane == 0) {
                     if (i == j) jb.d[j] = xi;
                     else { jb.x[i] = xi; if (i >= j + 2) nrm = fmaf(xi, xi, nrm); }
@@ -219,9 +239,18 @@ __device__ void run_job(const Job& jb, int rank, Smem& sm) {
         team_barrier(jb.bar, target, team);
         TRD_TICK(2);
         // ---------------- phase B: reflector, y = T v, panel inner products ----------------
-        reduce_partials(jb, sm, 65, 66);
+        const int c_al = (j + 1) & ~3;
+        constexpr int XR = MAXN / THREADS;
+        float xr[XR];                                            // raw column, in flight while |x|^2 is being reduced
+#pragma unroll
+        for (int u = 0; u < XR; ++u) {
+            const int c = c_al + tid + u * THREADS;
+            xr[u] = (c > j + 1 && c < n) ? __ldcg(jb.x + c) : 0.f;
+        }
         if (warp == 0) {
-            const float s2 = sm.q[65];
+            float s2 = 0.f;
+            for (int r = lane; r < team; r += 32) s2 += __ldcg(jb.part + 65 * TS + r);
+            s2 = warp_sum(s2);
             const float alpha = __ldcg(jb.x + j + 1);
             float beta, tau, scale;
             if (s2 == 0.f) { tau = 0.f; beta = alpha; scale = 0.f; }
@@ -236,14 +265,12 @@ __device__ void run_job(const Job& jb, int rank, Smem& sm) {
             }
         }
         __syncthreads();
-        const int c_al = (j + 1) & ~3;
         {
             const float scale = sm.scale;
-            for (int c = c_al + tid; c < ldt; c += THREADS) {
-                float val = 0.f;
-                if (c == j + 1) val = 1.f;
-                else if (c > j + 1 && c < n) val = __ldcg(jb.x + c) * scale;
-                sm.v[c] = val;
+#pragma unroll
+            for (int u = 0; u < XR; ++u) {
+                const int c = c_al + tid + u * THREADS;
+                if (c < ldt) sm.v[c] = (c == j + 1) ? 1.f : xr[u] * scale;
             }
         }
         __syncthreads();
@@ -253,30 +280,27 @@ __device__ void run_job(const Job& jb, int rank, Smem& sm) {
             const int q_beg = c_al >> 2, q_end = ldt >> 2;
             for (int i = first_own(j + 1, rank, team) + team * warp; i < n; i += team * NWARP) {
                 const float4* row = reinterpret_cast<const float4*>(jb.T + (size_t)i * ldt);
+                // panel rows of this matrix row: issued before the long product, consumed after it
+                const float wpi = lane < jp ? __ldcg(jb.Wp + (size_t)i * NB + lane) : 0.f;
+                const float vpi = lane < jp ? __ldcg(jb.Vp + (size_t)i * NB + lane) : 0.f;
                 float a0 = 0.f, a1 = 0.f;
-                int q = q_beg + lane;
-                for (; q + 96 < q_end; q += 128) {
-                    const float4 m0 = __ldcg(row + q), m1 = __ldcg(row + q + 32), m2 = __ldcg(row + q + 64), m3 = __ldcg(row + q + 96);
-                    const float4 v0 = *reinterpret_cast<const float4*>(&sm.v[4 * q]);
-                    const float4 v1 = *reinterpret_cast<const float4*>(&sm.v[4 * (q + 32)]);
-                    const float4 v2 = *reinterpret_cast<const float4*>(&sm.v[4 * (q + 64)]);
-                    const float4 v3 = *reinterpret_cast<const float4*>(&sm.v[4 * (q + 96)]);
-                    a0 = fmaf(m0.x, v0.x, fmaf(m0.y, v0.y, fmaf(m0.z, v0.z, fmaf(m0.w, v0.w, a0))));
-                    a1 = fmaf(m1.x, v1.x, fmaf(m1.y, v1.y, fmaf(m1.z, v1.z, fmaf(m1.w, v1.w, a1))));
-                    a0 = fmaf(m2.x, v2.x, fmaf(m2.y, v2.y, fmaf(m2.z, v2.z, fmaf(m2.w, v2.w, a0))));
-                    a1 = fmaf(m3.x, v3.x, fmaf(m3.y, v3.y, fmaf(m3.z, v3.z, fmaf(m3.w, v3.w, a1))));
-                }
-                for (; q < q_end; q += 32) {
-                    const float4 m0 = __ldcg(row + q);
-                    const float4 v0 = *reinterpret_cast<const float4*>(&sm.v[4 * q]);
-                    a0 = fmaf(m0.x, v0.x, fmaf(m0.y, v0.y, fmaf(m0.z, v0.z, fmaf(m0.w, v0.w, a0))));
+                for (int q = q_beg + lane; q < q_end; q += 256) {       // 8 predicated 16-byte loads in flight per lane
+                    float4 m[8];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u)
+                        m[u] = (q + 32 * u < q_end) ? __ldcg(row + q + 32 * u) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        const int qq = (q + 32 * u < q_end) ? q + 32 * u : q;
+                        const float4 vv = *reinterpret_cast<const float4*>(&sm.v[4 * qq]);
+                        const float t = fmaf(m[u].x, vv.x, fmaf(m[u].y, vv.y, fmaf(m[u].z, vv.z, m[u].w * vv.w)));
+                        if (u & 1) a1 += t; else a0 += t;
+                    }
                 }
                 const float yi = warp_sum(a0 + a1);
                 const float vi = sm.v[i];
-                if (lane < jp) {
-                    acc_s = fmaf(__ldcg(jb.Wp + (size_t)i * NB + lane), vi, acc_s);
-                    acc_t = fmaf(__ldcg(jb.Vp + (size_t)i * NB + lane), vi, acc_t);
-                }
+                acc_s = fmaf(wpi, vi, acc_s);
+                acc_t = fmaf(vpi, vi, acc_t);
                 if (lane == 0) {
                     jb.y[i] = yi;
                     acc_vy = fmaf(vi, yi, acc_vy);
@@ -302,7 +326,7 @@ __device__ void run_job(const Job& jb, int rank, Smem& sm) {
         TRD_TICK(6);
         // ---------------- panel end: finish w_j (rows > j), rank-2k update of the trailing square ----------------
         if (jp == NB - 1 || j == n - 2) {
-            reduce_partials(jb, sm, 0, 65);
+            reduce_st(jb, sm, jp);
             if (warp == 0) finish_prologue(jb, sm, jp, 0, false);
             __syncthreads();
             const float tau_p = sm.tau, cw = sm.cw;

@@ -8,7 +8,7 @@ namespace kfacb {
 namespace trd {
 
 constexpr int NB = 32;            // panel width = warp size: lane k owns panel column k
-constexpr int THREADS = 1024;
+constexpr int THREADS = 512;       // 128 registers per thread: 8 x 16-byte loads in flight per lane in the product
 constexpr int NWARP = THREADS / 32;
 constexpr int MAXN = 8192;        // the reflector vector of one column lives in shared memory
 constexpr int NPART = 66;         // partial sums per team member: [0,32) W^T v, [32,64) V^T v, [64] v.y, [65] |x|^2
@@ -52,5 +52,7 @@ cudaError_t launch_copy(const Job* d_jobs, const float* const* d_src, int njobs,
 size_t eigh_tdc_workspace_bytes(const int32_t* n, int count, const int* idx, int nb);
 int eigh_tdc_run(const int32_t* n, const int* idx, int nb, const float* const* M, float* const* Q, float* const* d,
                  float eps_floor, int32_t* sweeps_out, char* ws, size_t ws_bytes, cudaStream_t st);
+
+int eigh_tdc_last_profile(double* out8);
 
 }  // namespace kfacb

@@ -26,6 +26,19 @@ struct EpiEigDivide {
     }
 };
 
+// out = v, stored into the local slab AND into the same offset of every peer's slab (peer memory over NVLink):
+// the exchange of kfac_preconditioner_inv.py:164-175 fused into the producing GEMM (exchange.cu)
+constexpr int MAX_PEERS = 15;
+struct PeerDeltas { int n; long long d[MAX_PEERS]; };
+struct EpiStoreBcast {
+    float* C; long ldc; PeerDeltas peers;
+    __device__ __forceinline__ void operator()(int m, int n, float v) const {
+        float* p = C + (long)m * ldc + n;
+        *p = v;
+        for (int q = 0; q < peers.n; ++q) *reinterpret_cast<float*>(reinterpret_cast<char*>(p) + peers.d[q]) = v;
+    }
+};
+
 static size_t precond_buf_bytes(const kfacb_layer_t* layers, int count) {
     size_t mx = 0;
     for (int i = 0; i < count; ++i) {
@@ -131,13 +144,20 @@ static int check_precond_args(const kfacb_layer_t* layers, int32_t count, void* 
     return KFACB_OK;
 }
 
-extern "C" int kfacb_precond_eigen(const kfacb_layer_t* layers, int32_t count,
-                                   const float* const* QA, const float* const* QG,
-                                   const float* const* dA, const float* const* dG,
-                                   const float* const* wgrad, const float* const* bgrad,
-                                   float* const* out, float damping,
-                                   void* workspace, size_t workspace_bytes,
-                                   kfacb_stream_t stream) {
+static int make_peers(int32_t npeers, const int64_t* deltas, PeerDeltas& pd) {
+    KFACB_REQUIRE(npeers >= 0 && npeers <= MAX_PEERS && (npeers == 0 || deltas), "bad peer list");
+    pd.n = npeers;
+    for (int q = 0; q < npeers; ++q) pd.d[q] = (long long)deltas[q];
+    return KFACB_OK;
+}
+
+static int precond_eigen_impl(const kfacb_layer_t* layers, int32_t count,
+                              const float* const* QA, const float* const* QG,
+                              const float* const* dA, const float* const* dG,
+                              const float* const* wgrad, const float* const* bgrad,
+                              float* const* out, float damping, const PeerDeltas& pd,
+                              void* workspace, size_t workspace_bytes,
+                              kfacb_stream_t stream) {
     cudaStream_t st = (cudaStream_t)stream;
     int rc = check_precond_args(layers, count, workspace, workspace_bytes);
     if (rc) return rc;
@@ -163,20 +183,48 @@ extern "C" int kfacb_precond_eigen(const kfacb_layer_t* layers, int32_t count,
         KFACB_CHECK_CUDA(launch_gemm_auto(LdKContig{t1, (long)nA, nG, nA},
                                      LdKContig{QA[i], (long)nA, nA, nA},
                                      EpiStore{t0, (long)nA, 1.f, 0.f}, nG, nA, nA, st));
-        // out = QG T2
-        KFACB_CHECK_CUDA(launch_gemm_auto(LdKContig{QG[i], (long)nG, nG, nG},
-                                     LdMnContig{t0, (long)nA, nA, nG},
-                                     EpiStore{out[i], (long)nA, 1.f, 0.f}, nG, nA, nG, st));
+        // out = QG T2  (+ the same elements into every peer's slab when an exchange is attached)
+        if (pd.n > 0)
+            KFACB_CHECK_CUDA(launch_gemm_auto(LdKContig{QG[i], (long)nG, nG, nG}, LdMnContig{t0, (long)nA, nA, nG},
+                                              EpiStoreBcast{out[i], (long)nA, pd}, nG, nA, nG, st));
+        else
+            KFACB_CHECK_CUDA(launch_gemm_auto(LdKContig{QG[i], (long)nG, nG, nG}, LdMnContig{t0, (long)nA, nA, nG},
+                                              EpiStore{out[i], (long)nA, 1.f, 0.f}, nG, nA, nG, st));
     }
     return KFACB_OK;
 }
 
-extern "C" int kfacb_precond_inverse(const kfacb_layer_t* layers, int32_t count,
-                                     const float* const* invA, const float* const* invG,
-                                     const float* const* wgrad, const float* const* bgrad,
-                                     float* const* out,
-                                     void* workspace, size_t workspace_bytes,
-                                     kfacb_stream_t stream) {
+extern "C" int kfacb_precond_eigen(const kfacb_layer_t* layers, int32_t count,
+                                   const float* const* QA, const float* const* QG,
+                                   const float* const* dA, const float* const* dG,
+                                   const float* const* wgrad, const float* const* bgrad,
+                                   float* const* out, float damping,
+                                   void* workspace, size_t workspace_bytes,
+                                   kfacb_stream_t stream) {
+    PeerDeltas pd; pd.n = 0;
+    return precond_eigen_impl(layers, count, QA, QG, dA, dG, wgrad, bgrad, out, damping, pd, workspace, workspace_bytes, stream);
+}
+
+extern "C" int kfacb_precond_eigen_bcast(const kfacb_layer_t* layers, int32_t count,
+                                         const float* const* QA, const float* const* QG,
+                                         const float* const* dA, const float* const* dG,
+                                         const float* const* wgrad, const float* const* bgrad,
+                                         float* const* out, float damping,
+                                         int32_t npeers, const int64_t* peer_deltas,
+                                         void* workspace, size_t workspace_bytes,
+                                         kfacb_stream_t stream) {
+    PeerDeltas pd;
+    int rc = make_peers(npeers, peer_deltas, pd);
+    if (rc) return rc;
+    return precond_eigen_impl(layers, count, QA, QG, dA, dG, wgrad, bgrad, out, damping, pd, workspace, workspace_bytes, stream);
+}
+
+static int precond_inverse_impl(const kfacb_layer_t* layers, int32_t count,
+                                const float* const* invA, const float* const* invG,
+                                const float* const* wgrad, const float* const* bgrad,
+                                float* const* out, const PeerDeltas& pd,
+                                void* workspace, size_t workspace_bytes,
+                                kfacb_stream_t stream) {
     cudaStream_t st = (cudaStream_t)stream;
     int rc = check_precond_args(layers, count, workspace, workspace_bytes);
     if (rc) return rc;
@@ -192,12 +240,38 @@ extern "C" int kfacb_precond_inverse(const kfacb_layer_t* layers, int32_t count,
         KFACB_CHECK_CUDA(launch_gemm_auto(LdGrad{wgrad[i], bgrad[i], nG, dW, nA},
                                      LdMnContig{invA[i], (long)nA, nA, nA},
                                      EpiStore{t0, (long)nA, 1.f, 0.f}, nG, nA, nA, st));
-        // out = invG T
-        KFACB_CHECK_CUDA(launch_gemm_auto(LdKContig{invG[i], (long)nG, nG, nG},
-                                     LdMnContig{t0, (long)nA, nA, nG},
-                                     EpiStore{out[i], (long)nA, 1.f, 0.f}, nG, nA, nG, st));
+        // out = invG T  (+ peers)
+        if (pd.n > 0)
+            KFACB_CHECK_CUDA(launch_gemm_auto(LdKContig{invG[i], (long)nG, nG, nG}, LdMnContig{t0, (long)nA, nA, nG},
+                                              EpiStoreBcast{out[i], (long)nA, pd}, nG, nA, nG, st));
+        else
+            KFACB_CHECK_CUDA(launch_gemm_auto(LdKContig{invG[i], (long)nG, nG, nG}, LdMnContig{t0, (long)nA, nA, nG},
+                                              EpiStore{out[i], (long)nA, 1.f, 0.f}, nG, nA, nG, st));
     }
     return KFACB_OK;
+}
+
+extern "C" int kfacb_precond_inverse(const kfacb_layer_t* layers, int32_t count,
+                                     const float* const* invA, const float* const* invG,
+                                     const float* const* wgrad, const float* const* bgrad,
+                                     float* const* out,
+                                     void* workspace, size_t workspace_bytes,
+                                     kfacb_stream_t stream) {
+    PeerDeltas pd; pd.n = 0;
+    return precond_inverse_impl(layers, count, invA, invG, wgrad, bgrad, out, pd, workspace, workspace_bytes, stream);
+}
+
+extern "C" int kfacb_precond_inverse_bcast(const kfacb_layer_t* layers, int32_t count,
+                                           const float* const* invA, const float* const* invG,
+                                           const float* const* wgrad, const float* const* bgrad,
+                                           float* const* out,
+                                           int32_t npeers, const int64_t* peer_deltas,
+                                           void* workspace, size_t workspace_bytes,
+                                           kfacb_stream_t stream) {
+    PeerDeltas pd;
+    int rc = make_peers(npeers, peer_deltas, pd);
+    if (rc) return rc;
+    return precond_inverse_impl(layers, count, invA, invG, wgrad, bgrad, out, pd, workspace, workspace_bytes, stream);
 }
 
 static int fin_total_chunks(const kfacb_layer_t* layers, int count) {

@@ -37,11 +37,16 @@ class LayerDesc(C.Structure):
 EXPORTS = [
     'kfacb_version', 'kfacb_build_fingerprint', 'kfacb_launch_count', 'kfacb_last_error', 'kfacb_device_info', 'kfacb_layer_dA', 'kfacb_layer_dG',
     'kfacb_factor_workspace_bytes', 'kfacb_factor_update',
-    'kfacb_eigh_workspace_bytes', 'kfacb_eigh_batched', 'kfacb_eigh_last_profile',
+    'kfacb_eigh_workspace_bytes', 'kfacb_eigh_batched', 'kfacb_eigh_last_profile', 'kfacb_eigh_plan_teams',
     'kfacb_spd_inverse_workspace_bytes', 'kfacb_pi_damped_inverse',
     'kfacb_precond_workspace_bytes', 'kfacb_precond_eigen', 'kfacb_precond_inverse',
     'kfacb_finalize_workspace_bytes', 'kfacb_finalize_grads',
+    'kfacb_precond_eigen_bcast', 'kfacb_precond_inverse_bcast',
+    'kfacb_exchange_create', 'kfacb_exchange_handle', 'kfacb_exchange_connect', 'kfacb_exchange_slab',
+    'kfacb_exchange_peer_deltas', 'kfacb_exchange_begin', 'kfacb_exchange_signal', 'kfacb_exchange_push',
+    'kfacb_exchange_wait', 'kfacb_exchange_release', 'kfacb_exchange_destroy',
 ]
+EXCHANGE_HANDLE_BYTES = 128
 
 _lib = None
 
@@ -82,6 +87,8 @@ def load_library(path: Optional[str] = None):
     lib.kfacb_eigh_batched.argtypes = [I32P, C.c_int32, PP, PP, PP, C.c_float, C.c_void_p,
                                        C.c_void_p, C.c_size_t, C.c_void_p]
     lib.kfacb_eigh_last_profile.argtypes = [C.POINTER(C.c_double)]
+    lib.kfacb_eigh_plan_teams.argtypes = [I32P, C.c_int32, C.c_int32, I32P]
+    lib.kfacb_eigh_plan_teams.restype = C.c_int
     lib.kfacb_spd_inverse_workspace_bytes.argtypes = [I32P, I32P, C.c_int32]
     lib.kfacb_spd_inverse_workspace_bytes.restype = C.c_size_t
     lib.kfacb_pi_damped_inverse.argtypes = [I32P, I32P, C.c_int32, PP, PP, PP, PP, C.c_float,
@@ -96,6 +103,21 @@ def load_library(path: Optional[str] = None):
     lib.kfacb_finalize_workspace_bytes.restype = C.c_size_t
     lib.kfacb_finalize_grads.argtypes = [LP, C.c_int32, PP, PP, PP, C.c_float, C.c_float,
                                          C.c_int32, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
+    I64P = C.POINTER(C.c_int64)
+    lib.kfacb_precond_eigen_bcast.argtypes = [LP, C.c_int32, PP, PP, PP, PP, PP, PP, PP, C.c_float, C.c_int32, I64P,
+                                              C.c_void_p, C.c_size_t, C.c_void_p]
+    lib.kfacb_precond_inverse_bcast.argtypes = [LP, C.c_int32, PP, PP, PP, PP, PP, C.c_int32, I64P,
+                                                C.c_void_p, C.c_size_t, C.c_void_p]
+    lib.kfacb_exchange_create.argtypes = [C.c_int32, C.c_int32, C.c_size_t, C.POINTER(C.c_void_p)]
+    lib.kfacb_exchange_handle.argtypes = [C.c_void_p, C.c_void_p]
+    lib.kfacb_exchange_connect.argtypes = [C.c_void_p, C.c_void_p]
+    lib.kfacb_exchange_slab.argtypes = [C.c_void_p]
+    lib.kfacb_exchange_slab.restype = C.c_void_p
+    lib.kfacb_exchange_peer_deltas.argtypes = [C.c_void_p, I64P, I32P]
+    for fn in ('begin', 'signal', 'wait', 'release'):
+        getattr(lib, 'kfacb_exchange_' + fn).argtypes = [C.c_void_p, C.c_void_p]
+    lib.kfacb_exchange_push.argtypes = [C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p]
+    lib.kfacb_exchange_destroy.argtypes = [C.c_void_p]
     for name in EXPORTS:
         getattr(lib, name)
     if path is None:
@@ -196,7 +218,10 @@ class NativeEngine:
         """Totals of the last KFACB_PROFILE=1 eigh call (see include/kfacb.h)."""
         out = (C.c_double * 8)()
         self._call(self.lib.kfacb_eigh_last_profile(out))
-        keys = ('rounds', 'ms_h', 'ms_solve', 'ms_update', 'bytes_h', 'bytes_update', 'matrices', 'pairs')
+        if os.environ.get('KFACB_EIGH_ALGO', '')[:1] in ('j', 'J'):
+            keys = ('rounds', 'ms_h', 'ms_solve', 'ms_update', 'bytes_h', 'bytes_update', 'matrices', 'pairs')
+        else:   # tridiagonalisation + divide and conquer: stage times of the last call (CUDA events; synchronises on them)
+            keys = ('ms_trd', 'ms_dc', 'ms_bt', 'bytes_trd', 'sum_n3', 'matrices', 'grid', 'reserved')
         return dict(zip(keys, list(out)))
 
     # -- (2b) pi-damped inverse ---------------------------------------------
@@ -214,7 +239,12 @@ class NativeEngine:
                 ws.data_ptr(), ws.numel(), self._stream()))
 
     # -- (3) preconditioning -------------------------------------------------
-    def precond_eigen(self, layers, QA, QG, dA, dG, wgrad, bgrad, out, damping: float):
+    @staticmethod
+    def _peer_args(peer_deltas):
+        k = len(peer_deltas) if peer_deltas else 0
+        return k, (C.c_int64 * max(1, k))(*(peer_deltas or []))
+
+    def precond_eigen(self, layers, QA, QG, dA, dG, wgrad, bgrad, out, damping: float, peer_deltas=None):
         for t in list(QA) + list(QG) + list(dA) + list(dG) + list(wgrad) + list(bgrad) + list(out):
             _check_f32(t, 'precond operand')
         d = _descs(layers)
@@ -222,11 +252,17 @@ class NativeEngine:
         nbytes = self.lib.kfacb_precond_workspace_bytes(d, n)
         ws = self._workspace('precond', nbytes)
         with torch.cuda.device(self.device):
-            self._call(self.lib.kfacb_precond_eigen(
-                d, n, _ptrs(QA), _ptrs(QG), _ptrs(dA), _ptrs(dG), _ptrs(wgrad), _ptrs(bgrad),
-                _ptrs(out), damping, ws.data_ptr(), ws.numel(), self._stream()))
+            if peer_deltas:      # fused exchange: the last GEMM's epilogue also stores into every peer's slab
+                k, arr = self._peer_args(peer_deltas)
+                self._call(self.lib.kfacb_precond_eigen_bcast(
+                    d, n, _ptrs(QA), _ptrs(QG), _ptrs(dA), _ptrs(dG), _ptrs(wgrad), _ptrs(bgrad),
+                    _ptrs(out), damping, k, arr, ws.data_ptr(), ws.numel(), self._stream()))
+            else:
+                self._call(self.lib.kfacb_precond_eigen(
+                    d, n, _ptrs(QA), _ptrs(QG), _ptrs(dA), _ptrs(dG), _ptrs(wgrad), _ptrs(bgrad),
+                    _ptrs(out), damping, ws.data_ptr(), ws.numel(), self._stream()))
 
-    def precond_inverse(self, layers, invA, invG, wgrad, bgrad, out):
+    def precond_inverse(self, layers, invA, invG, wgrad, bgrad, out, peer_deltas=None):
         for t in list(invA) + list(invG) + list(wgrad) + list(bgrad) + list(out):
             _check_f32(t, 'precond operand')
         d = _descs(layers)
@@ -234,9 +270,15 @@ class NativeEngine:
         nbytes = self.lib.kfacb_precond_workspace_bytes(d, n)
         ws = self._workspace('precond', nbytes)
         with torch.cuda.device(self.device):
-            self._call(self.lib.kfacb_precond_inverse(
-                d, n, _ptrs(invA), _ptrs(invG), _ptrs(wgrad), _ptrs(bgrad), _ptrs(out),
-                ws.data_ptr(), ws.numel(), self._stream()))
+            if peer_deltas:
+                k, arr = self._peer_args(peer_deltas)
+                self._call(self.lib.kfacb_precond_inverse_bcast(
+                    d, n, _ptrs(invA), _ptrs(invG), _ptrs(wgrad), _ptrs(bgrad), _ptrs(out), k, arr,
+                    ws.data_ptr(), ws.numel(), self._stream()))
+            else:
+                self._call(self.lib.kfacb_precond_inverse(
+                    d, n, _ptrs(invA), _ptrs(invG), _ptrs(wgrad), _ptrs(bgrad), _ptrs(out),
+                    ws.data_ptr(), ws.numel(), self._stream()))
 
     # -- (4) KL clip + in-place rewrite ----------------------------------------
     def finalize(self, layers, precon, wgrad, bgrad, lr: float, kl_clip: Optional[float],
@@ -252,3 +294,68 @@ class NativeEngine:
                 d, n, _ptrs(precon), _ptrs(wgrad), _ptrs(bgrad), lr,
                 float(kl_clip) if kl_clip else 0.0, int(force_nu_one), nu_out.data_ptr(),
                 ws.data_ptr(), ws.numel(), self._stream()))
+
+
+class _RawCudaBuffer:
+    """Exposes library-owned device memory to torch (zero copy) through ``__cuda_array_interface__``."""
+
+    def __init__(self, ptr: int, nfloats: int):
+        self.__cuda_array_interface__ = dict(shape=(nfloats,), typestr='<f4', data=(ptr, False), version=2)
+
+
+class Exchange:
+    """``kfacb_exchange_*``: the symmetric slab of preconditioned gradients of the ranks of one node (CUDA IPC peer
+    memory) and its begin / signal / push / wait / release flag kernels (include/kfacb.h section 3b)."""
+
+    def __init__(self, engine: NativeEngine, rank: int, size: int, nfloats: int):
+        self.eng, self.lib = engine, engine.lib
+        self.rank, self.size, self.nfloats = rank, size, int(nfloats)
+        self._h = C.c_void_p()
+        with torch.cuda.device(engine.device):
+            engine._call(self.lib.kfacb_exchange_create(rank, size, self.nfloats * 4, C.byref(self._h)))
+            ptr = self.lib.kfacb_exchange_slab(self._h)
+            self.slab = torch.as_tensor(_RawCudaBuffer(ptr, max(1, self.nfloats)), device=engine.device)
+        self.peer_deltas: List[int] = []
+
+    def handle(self) -> bytes:
+        buf = (C.c_ubyte * EXCHANGE_HANDLE_BYTES)()
+        with torch.cuda.device(self.eng.device):
+            self.eng._call(self.lib.kfacb_exchange_handle(self._h, buf))
+        return bytes(buf)
+
+    def connect(self, handles: Sequence[bytes]):
+        assert len(handles) == self.size and all(len(h) == EXCHANGE_HANDLE_BYTES for h in handles)
+        blob = b''.join(handles)
+        buf = (C.c_ubyte * len(blob)).from_buffer_copy(blob)
+        with torch.cuda.device(self.eng.device):
+            self.eng._call(self.lib.kfacb_exchange_connect(self._h, buf))
+            d = (C.c_int64 * max(1, self.size))()
+            k = C.c_int32()
+            self.eng._call(self.lib.kfacb_exchange_peer_deltas(self._h, d, C.byref(k)))
+        self.peer_deltas = [int(d[i]) for i in range(k.value)]
+
+    def _op(self, name):
+        with torch.cuda.device(self.eng.device):
+            self.eng._call(getattr(self.lib, 'kfacb_exchange_' + name)(self._h, self.eng._stream()))
+
+    def begin(self):
+        self._op('begin')
+
+    def signal(self):
+        self._op('signal')
+
+    def wait(self):
+        self._op('wait')
+
+    def release(self):
+        self._op('release')
+
+    def push(self, offset_floats: int, nfloats: int):
+        with torch.cuda.device(self.eng.device):
+            self.eng._call(self.lib.kfacb_exchange_push(self._h, offset_floats * 4, nfloats * 4, self.eng._stream()))
+
+    def close(self):
+        if self._h:
+            self.slab = None
+            self.lib.kfacb_exchange_destroy(self._h)
+            self._h = C.c_void_p()

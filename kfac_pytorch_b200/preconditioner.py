@@ -160,6 +160,8 @@ class KFAC(optim.Optimizer):
         self._engine = engine
         self._static = [_static_desc(m) for m in self.modules]
         self._slab = None
+        self._ex = None
+        self._ex_fused = False
         self._slab_segments = None
         self._nu = None
         # factor-wise distribution of the MPD eigen variant (eigen.py:66-71)
@@ -369,9 +371,24 @@ class KFAC(optim.Optimizer):
             backend.comm.synchronize(h)
 
     # ---------------------------------------------------------------- phase 3
+    def _exchange_mode(self) -> str:
+        """'p2p' (default for the DP variants when every rank sits on this node: symmetric slab over CUDA IPC peer
+        memory, transfer fused into the last preconditioning GEMM), or 'nccl' (one broadcast per owner rank over
+        the same slab layout).  KFACB_EXCHANGE overrides."""
+        import os
+        mode = os.environ.get('KFACB_EXCHANGE', '').lower()
+        if mode in ('p2p', 'nccl', 'p2p_push'):
+            return mode
+        size = backend.comm.size()
+        local = int(os.environ.get('LOCAL_WORLD_SIZE', '0') or 0)
+        if self.is_dp and size > 1 and local == size and self._device().type == 'cuda':
+            return 'p2p'
+        return 'nccl'
+
     def _ensure_slab(self):
         """One flat buffer for all preconditioned gradients, laid out so that each
-        owner rank's layers are contiguous: the exchange is one broadcast per rank."""
+        owner rank's layers are contiguous: the exchange is one broadcast per rank
+        (NCCL mode) or lands in every peer's copy while it is produced (P2P mode)."""
         if self._slab is not None:
             return
         dev = self._device()
@@ -385,14 +402,31 @@ class KFAC(optim.Optimizer):
             if seg[r][0] is None:
                 seg[r][0] = off
             offs[i] = off
-            off += n
+            off += (n + 3) & ~3                 # 16-byte aligned layers (vector copies of kfacb_exchange_push)
             seg[r][1] = off
-        self._slab = torch.zeros(max(off, 1), dtype=torch.float32, device=dev)
+        self._ex = None
+        mode = self._exchange_mode() if (size > 1 and self.is_dp) else 'nccl'
+        if mode.startswith('p2p'):
+            import torch.distributed as dist
+            from .native import Exchange
+            ex = Exchange(self._get_engine(), backend.comm.rank(), size, max(off, 4))
+            handles = [None] * size
+            dist.all_gather_object(handles, ex.handle())
+            ex.connect(handles)
+            self._ex, self._ex_fused = ex, mode == 'p2p'
+            self._slab = ex.slab
+        else:
+            self._slab = torch.zeros(max(off, 1), dtype=torch.float32, device=dev)
         self._slab_segments = seg
         for i, m in enumerate(self.modules):
             d = self._static[i]
             self.m_precon_grad[m] = self._slab[offs[i]:offs[i] + d.dA * d.dG].view(d.dG, d.dA)
         self._nu = torch.ones(1, dtype=torch.float32, device=dev)
+
+    def _use_exchange(self) -> bool:
+        # the ablation flag exclude_parts='CommunicateInverse' must really skip the exchange (kfac_preconditioner_base.py:214-217)
+        return (getattr(self, '_ex', None) is not None and not self.exclude_communicate_inverse
+                and not self.communicate_inverse_or_not)
 
     def _grads(self, idx):
         w, b = [], []
@@ -420,24 +454,36 @@ class KFAC(optim.Optimizer):
         # DP: owner only.  MPD: every rank multiplies every layer with whatever inverse it holds
         # (zeros on non-owners unless the inverses were broadcast; inv.py:156-161, eigen.py:137-144)
         owned = self._owned() if self.is_dp else list(range(len(self.modules)))
-        if not owned:
-            return
-        descs = [self._static[i] for i in owned]
-        w, b = self._grads(owned)
-        out = [self.m_precon_grad[self.modules[i]] for i in owned]
-        mods = [self.modules[i] for i in owned]
-        if self.uses_eigen:
-            eng.precond_eigen(descs, [self.m_QA[m] for m in mods], [self.m_QG[m] for m in mods],
-                              [self.m_dA[m] for m in mods], [self.m_dG[m] for m in mods],
-                              w, b, out, self.damping)
-        else:
-            eng.precond_inverse(descs, [self.m_inv_A[m] for m in mods],
-                                [self.m_inv_G[m] for m in mods], w, b, out)
+        use_ex = self._use_exchange()
+        if use_ex:
+            self._ex.begin()                   # every peer has finished reading the previous step's slab
+        if owned:
+            descs = [self._static[i] for i in owned]
+            w, b = self._grads(owned)
+            out = [self.m_precon_grad[self.modules[i]] for i in owned]
+            mods = [self.modules[i] for i in owned]
+            deltas = self._ex.peer_deltas if (use_ex and self._ex_fused) else None
+            if self.uses_eigen:
+                eng.precond_eigen(descs, [self.m_QA[m] for m in mods], [self.m_QG[m] for m in mods],
+                                  [self.m_dA[m] for m in mods], [self.m_dG[m] for m in mods],
+                                  w, b, out, self.damping, peer_deltas=deltas)
+            else:
+                eng.precond_inverse(descs, [self.m_inv_A[m] for m in mods],
+                                    [self.m_inv_G[m] for m in mods], w, b, out, peer_deltas=deltas)
+        if use_ex:
+            if self._ex_fused:
+                self._ex.signal()              # my segment has landed in every peer's slab
+            else:
+                beg, end = self._slab_segments[backend.comm.rank()]
+                self._ex.push(beg or 0, 0 if beg is None else end - beg)
 
     def _communicate_pred(self):
         """Owner -> everyone exchange of the preconditioned gradients.  The reference
         issues one broadcast per layer (kfac_preconditioner_inv.py:164-175); the slab
         layout makes it one broadcast per owner rank."""
+        if self._use_exchange():
+            self._ex.wait()                    # every peer's segment has landed in the local slab
+            return
         handles = []
         for r, (beg, end) in enumerate(self._slab_segments):
             if beg is None:
@@ -456,6 +502,8 @@ class KFAC(optim.Optimizer):
         eng.finalize(self._static, [self.m_precon_grad[m] for m in self.modules], w, b,
                      float(self.lr), self.kl_clip,
                      self.kl_clip is not None and self.exclude_communicate_inverse, self._nu)
+        if self._use_exchange() and backend.comm.size() > 1:
+            self._ex.release()                 # peers may overwrite the local slab from now on
 
     # ------------------------------------------------------ K-FAC state (resume)
     def kfac_state_dict(self):

@@ -43,12 +43,12 @@ class OracleEngine:
             Ad, Gd, a_inv, g_inv = orc.pi_damped_inverses(Ai, Gi, damping)
             Ai.copy_(Ad); Gi.copy_(Gd); iA.copy_(a_inv); iG.copy_(g_inv)
 
-    def precond_eigen(self, layers, QA, QG, dA, dG, wgrad, bgrad, out, damping):
+    def precond_eigen(self, layers, QA, QG, dA, dG, wgrad, bgrad, out, damping, peer_deltas=None):
         for d, qa, qg, da, dg, w, b, o in zip(layers, QA, QG, dA, dG, wgrad, bgrad, out):
             gm = orc.grad_matrix(spec_of(d), w, b)
             o.copy_(orc.precondition_eigen(gm, qa, da, qg, dg, damping))
 
-    def precond_inverse(self, layers, invA, invG, wgrad, bgrad, out):
+    def precond_inverse(self, layers, invA, invG, wgrad, bgrad, out, peer_deltas=None):
         for d, ia, ig, w, b, o in zip(layers, invA, invG, wgrad, bgrad, out):
             gm = orc.grad_matrix(spec_of(d), w, b)
             o.copy_(orc.precondition_inverse(gm, ia, ig))

@@ -85,44 +85,83 @@ R50_LAYER_CLASSES = [
 ]
 
 
-@pytest.mark.parametrize('cls', R50_LAYER_CLASSES, ids=lambda c: c[2].split(':')[0].replace(' ', '_'))
-def test_resnet50_layer_step_vs_oracle_at_full_size(cls):
-    """Whole step() (factors -> eigh -> two-sided product -> KL clip) of ONE ResNet-50 layer at the BASELINE
-    batch size, 2 steps, against the oracle in fp64 (truth) and fp32 (the reference's own noise)."""
+VGG_BERT_LAYER_CLASSES = [
+    # (variant, hyper-parameters of the reference's train_*.sh, module ctor, input H=W, seq, batch, steps, what)
+    ('inverse_dp', dict(lr=0.1, damping=0.03, kl_clip=0.001), lambda: torch.nn.Conv2d(512, 512, 3, padding=1), 2, None, 128, 3,
+     'vgg16 conv 512->512 @2x2 +bias: dA=4609, dG=512, rows=512, damping accumulates over 3 steps'),
+    ('inverse_dp', dict(lr=0.1, damping=0.03, kl_clip=0.001), lambda: torch.nn.Conv2d(256, 256, 3, padding=1), 8, None, 128, 3,
+     'vgg16 conv 256->256 @8x8 +bias: dA=2305, dG=256, rows=8192'),
+    ('eigen_dp', dict(lr=3e-5, damping=0.03, kl_clip=None), lambda: torch.nn.Linear(3072, 768), None, 384, 8, 2,
+     'bert ffn-out 3072->768, (B,T,D) input, kl_clip=None: dA=3073, dG=768'),
+    ('eigen_dp', dict(lr=3e-5, damping=0.03, kl_clip=None), lambda: torch.nn.Linear(768, 3072), None, 384, 8, 2,
+     'bert ffn-in 768->3072, (B,T,D) input: dA=769, dG=3072'),
+]
+
+
+def _layer_step_vs_oracle(variant, hyper, ctor, hw, seq, batch, steps, what):
+    """Whole step() of ONE layer at the BASELINE batch size against the oracle in fp64 (truth) and fp32
+    (the reference's own noise).  Returns (our error, reference fp32 noise)."""
     import kfac_pytorch_b200 as kfac
     from kfac_pytorch_b200 import backend
     from oracle.kfac_oracle import (OracleDPKFAC, specs_from_model, synth_grads, synth_layer_inputs)
-    ctor, hw, what = cls
     backend.comm = None
     torch.manual_seed(0)
     mod = ctor()
     model = torch.nn.Sequential(mod)
     specs, mods = specs_from_model(model)
     spec = specs[0]
-    hyper = dict(lr=0.0125, damping=0.002, kl_clip=0.001)
     torch.set_num_threads(16)
+    hwt = None if hw is None else (hw, hw)
     res = {}
     for tag, dt in (('f64', torch.float64), ('f32', torch.float32)):
-        orc_ = OracleDPKFAC([spec], variant='eigen_dp', **hyper)
-        for s in range(2):
+        orc_ = OracleDPKFAC([spec], variant=variant, **hyper)
+        for s in range(steps):
             gen = torch.Generator().manual_seed(100 + s)
-            li = synth_layer_inputs(spec, 32, None if hw is None else (hw, hw), None, gen, dt)
+            li = synth_layer_inputs(spec, batch, hwt, seq, gen, dt)
             w, b = synth_grads(spec, gen, dt)
             ow, ob = orc_.step([[li]], [w], [b])
-        res[tag] = ow[0].double()
+        res[tag] = torch.cat([ow[0].double().reshape(-1)] + ([] if ob[0] is None else [ob[0].double().reshape(-1)]))
     model.to(DEV)
-    pre = kfac.get_kfac_module('eigen_dp')(model, hook_enabled=False, **hyper)
-    for s in range(2):
+    pre = kfac.get_kfac_module(variant)(model, hook_enabled=False, **hyper)
+    for s in range(steps):                           # back to back: no host synchronisation between the steps
         gen = torch.Generator().manual_seed(100 + s)
-        li = synth_layer_inputs(spec, 32, None if hw is None else (hw, hw), None, gen)
+        li = synth_layer_inputs(spec, batch, hwt, seq, gen)
         w, b = synth_grads(spec, gen)
         pre.m_a[mod] = li.a.to(DEV); pre.m_g[mod] = li.g.to(DEV)
         mod.weight.grad = w.to(DEV)
         if b is not None:
             mod.bias.grad = b.to(DEV)
         pre.step()
-    ours = mod.weight.grad.double().cpu()
+    ours = torch.cat([mod.weight.grad.double().cpu().reshape(-1)] +
+                     ([] if mod.bias is None else [mod.bias.grad.double().cpu().reshape(-1)]))
     noise = ((res['f32'] - res['f64']).norm() / res['f64'].norm()).item()
     err = ((ours - res['f64']).norm() / res['f64'].norm()).item()
-    print('\nFULLSIZE %-45s ours-vs-fp64 %.2e   reference-fp32-vs-fp64 %.2e' % (what, err, noise))
+    line = 'FULLSIZE %-14s %-80s ours-vs-fp64 %.2e   reference-fp32-vs-fp64 %.2e' % (variant, what, err, noise)
+    print('\n' + line)
+    try:                                              # evidence file for profiles/ (best effort)
+        import os
+        os.makedirs('gpurun_out', exist_ok=True)
+        with open('gpurun_out/r02_parity.txt', 'a') as fh:
+            fh.write(line + '\n')
+    except OSError:
+        pass
+    return err, noise
+
+
+@pytest.mark.parametrize('cls', VGG_BERT_LAYER_CLASSES, ids=lambda c: c[7].split(':')[0].replace(' ', '_').replace(',', ''))
+def test_vgg16_bert_layer_step_vs_oracle_at_full_size(cls):
+    """BASELINE configs 4 and 5 at full factor size: VGG-16 `inverse_dp` (dA = 4609 / 2305 with bias; the pi-damping is
+    added to the running factor IN PLACE every step, kfac_preconditioner_inv_dp.py:98-123) and BERT-base `eigen_dp`
+    ((B,T,D) inputs averaged over T, kfac/utils.py:98-99; n = 3073 / 3072; kl_clip=None)."""
+    variant, hyper, ctor, hw, seq, batch, steps, what = cls
+    err, noise = _layer_step_vs_oracle(variant, hyper, ctor, hw, seq, batch, steps, what)
+    assert err <= max(1e-4, 3 * noise), (what, err, noise)
+
+
+@pytest.mark.parametrize('cls', R50_LAYER_CLASSES, ids=lambda c: c[2].split(':')[0].replace(' ', '_'))
+def test_resnet50_layer_step_vs_oracle_at_full_size(cls):
+    """Whole step() (factors -> eigh -> two-sided product -> KL clip) of ONE ResNet-50 layer at the BASELINE
+    batch size, 2 steps back to back, against the oracle in fp64 (truth) and fp32 (the reference's own noise)."""
+    ctor, hw, what = cls
+    err, noise = _layer_step_vs_oracle('eigen_dp', dict(lr=0.0125, damping=0.002, kl_clip=0.001), ctor, hw, None, 32, 2, what)
     assert err <= max(1e-4, 3 * noise), (what, err, noise)

@@ -85,7 +85,7 @@ def test_c_abi_exports_every_declared_symbol():
     from kfac_pytorch_b200 import build, native
     build.build(verbose=False)
     hdr = open(os.path.join(ROOT, 'include', 'kfacb.h')).read()
-    declared = set(re.findall(r'^\s*(?:int|size_t|int32_t|uint64_t|const char\*)\s+(kfacb_\w+)\s*\(', hdr, re.M))
+    declared = set(re.findall(r'^\s*(?:int|size_t|int32_t|uint64_t|const char\*|void\*)\s+(kfacb_\w+)\s*\(', hdr, re.M))
     assert declared == set(native.EXPORTS), declared ^ set(native.EXPORTS)
     lib = ctypes.CDLL(native.LIB_PATH)
     for name in declared:
@@ -221,3 +221,27 @@ def test_kfac_state_round_trip_resumes_bit_identically():
     resumed, _ = run(resume_at=2, state=saved)
     for a, b in zip(full, resumed):
         assert torch.equal(a, b)
+
+
+def test_eigh_team_scheduler_is_sane_for_resnet50():
+    """kfacb_eigh_plan_teams (no GPU needed): every n > 128 factor gets a team, the persistent kernel never asks for
+    more CTAs than the device has SMs, and the big factors get the big teams."""
+    from kfac_pytorch_b200 import native
+    from kfac_pytorch_b200.workloads import layer_dims, resnet50_layers
+    lib = native.load_library()
+    ns = []
+    for ls in resnet50_layers():
+        ns += list(layer_dims(ls))
+    for sms in (148, 132, 20):
+        arr = (ctypes.c_int32 * len(ns))(*ns)
+        out = (ctypes.c_int32 * len(ns))()
+        grid = lib.kfacb_eigh_plan_teams(arr, len(ns), sms, out)
+        assert 0 < grid <= sms
+        for n, t in zip(ns, out):
+            assert (t == 0) == (n <= 128) and t <= sms
+        big = max(t for n, t in zip(ns, out) if n == 4608)
+        assert all(t <= big for t in out)
+    assert lib.kfacb_eigh_workspace_bytes(arr, len(ns)) > 4 * sum(4 * n * n for n in ns if n > 128)
+    lone = (ctypes.c_int32 * 1)(4608)
+    out1 = (ctypes.c_int32 * 1)()
+    assert lib.kfacb_eigh_plan_teams(lone, 1, 148, out1) == out1[0] >= 64      # a lone big factor gets most of the GPU

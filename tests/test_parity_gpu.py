@@ -33,40 +33,40 @@ def test_golden_case_cuda(case):
     print(case.name, {k: f'{v:.1e}' for k, v in report.items()})
 
 
-def _ws2_cuda_worker(rank, case_name, port, q):
+def _ws2_cuda_worker(rank, case_name, port, q, transport, exchange):
     sys.path.insert(0, ROOT)
     import torch.distributed as dist
     from kfac_pytorch_b200 import backend
     os.environ['MASTER_ADDR'] = '127.0.0.1'
     os.environ['MASTER_PORT'] = str(port)
     os.environ['LOCAL_RANK'] = str(rank)
+    os.environ['KFACB_EXCHANGE'] = exchange
     ngpu = torch.cuda.device_count()
     dev = torch.device('cuda', rank % ngpu)
     torch.cuda.set_device(dev)
-    # two ranks may share one GPU in this test, which NCCL forbids -> gloo moves the CUDA slabs
-    dist.init_process_group('nccl' if ngpu >= 2 else 'gloo', rank=rank, world_size=2)
+    dist.init_process_group(transport, rank=rank, world_size=2)
     backend.comm = None
     backend.init('Torch')
     case = CASES_BY_NAME[case_name]
     out, pre = run_package_case(case, dev, rank=rank)
     torch.cuda.synchronize()
-    q.put((rank, out))
+    used = 'p2p' if getattr(pre, '_ex', None) is not None else 'broadcast'
+    q.put((rank, out, used))
     dist.barrier()
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize('case', [c for c in CASES if c.world_size == 2], ids=lambda c: c.name)
-def test_golden_case_cuda_world_size_2(case):
+def _run_ws2(case, transport, exchange):
     ctx = mp.get_context('spawn')
     q = ctx.Queue()
-    port = 29900 + (abs(hash(case.name)) % 90)
-    procs = [ctx.Process(target=_ws2_cuda_worker, args=(r, case.name, port, q)) for r in range(2)]
+    port = 29900 + (abs(hash((case.name, transport, exchange))) % 90)
+    procs = [ctx.Process(target=_ws2_cuda_worker, args=(r, case.name, port, q, transport, exchange)) for r in range(2)]
     for p in procs:
         p.start()
-    res = {}
+    res, used = {}, {}
     for _ in procs:
-        rank, out = q.get(timeout=600)
-        res[rank] = out
+        rank, out, u = q.get(timeout=600)
+        res[rank], used[rank] = out, u
     for p in procs:
         p.join(timeout=60)
     for rank in (0, 1):
@@ -74,6 +74,35 @@ def test_golden_case_cuda_world_size_2(case):
     for k, v in res[0].items():
         if k.endswith('wgrad') or k.endswith('bgrad'):
             np.testing.assert_array_equal(v, res[1][k.replace('r0_', 'r1_', 1)])
+    return used
+
+
+WS2_CASES = [c for c in CASES if c.world_size == 2]
+
+
+@pytest.mark.parametrize('case', WS2_CASES, ids=lambda c: c.name)
+def test_golden_case_cuda_world_size_2(case):
+    """Two ranks sharing cuda:0 (NCCL forbids that, so gloo moves the CUDA slabs): runs on the 1-GPU box."""
+    _run_ws2(case, 'gloo', 'nccl')
+
+
+@pytest.mark.parametrize('case', WS2_CASES, ids=lambda c: c.name)
+def test_golden_case_cuda_world_size_2_nccl_two_gpus(case):
+    """The same cases with one rank per GPU over NCCL; SKIPPED (never a silent gloo fallback) on a 1-GPU box."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip('needs 2 GPUs (gpurun --gpus 2)')
+    _run_ws2(case, 'nccl', 'nccl')
+
+
+@pytest.mark.parametrize('exchange', ['p2p', 'p2p_push'])
+@pytest.mark.parametrize('case', [c for c in WS2_CASES if c.variant.endswith('_dp')], ids=lambda c: c.name)
+def test_golden_case_cuda_world_size_2_peer_memory_exchange(case, exchange):
+    """kfacb_exchange_*: the symmetric slab over CUDA IPC peer memory -- fused into the last preconditioning GEMM's
+    epilogue ('p2p') or as one push kernel ('p2p_push').  Two processes; with one GPU they share it (the IPC mapping
+    and the flag protocol are the same, only the wire is missing), with two GPUs the stores cross NVLink."""
+    transport = 'nccl' if torch.cuda.device_count() >= 2 else 'gloo'
+    used = _run_ws2(case, transport, exchange)
+    assert used == {0: 'p2p', 1: 'p2p'}
 
 
 def test_hook_path_matches_reference_fixture():
