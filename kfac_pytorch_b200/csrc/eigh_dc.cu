@@ -35,7 +35,7 @@ namespace dc {
 
 constexpr int LEAF = 64;
 constexpr int PB = 128;                  // reflectors per block reflector of the back-transformation
-constexpr int YCH = 256;                 // split-K chunk of Y = Zt V^T (bounds the in-TMEM accumulation chain)
+constexpr int YCH = 512;                 // split-K chunk of Y = Zt V^T (bounds the in-TMEM accumulation chain)
 constexpr float FEPS = 5.9604645e-8f;    // 2^-24
 
 struct DcMat {
@@ -93,6 +93,37 @@ dc_leaf_kernel(const DcMat* mats, const DcLeaf* leaves) {
     }
     __syncthreads();
     jacobi_smem<0>(S, U, m, P, 1.2e-7f, 1.5e-8f * s_scale, 1e30f, 30, nullptr);
+    __syncthreads();
+    // ~400 fp32 rotations per column leave U orthogonal only to ~4e-6; every merge above inherits that.  One
+    // Newton-Schulz step  U <- U (I - (U^T U - I) / 2)  in shared memory (2 m^3 flops) brings it to ~2e-7.
+    for (int e = tid; e < m * m; e += nt) {
+        const int i = e / m, j = e - i * m;
+        float acc = 0.f;
+        for (int k = 0; k < m; ++k) acc = fmaf(U[k * P + i], U[k * P + j], acc);
+        S[i * P + j] = acc - (i == j ? 1.f : 0.f);
+    }
+    __syncthreads();
+    {
+        constexpr int PER = (LEAF_MAX * LEAF_MAX + 255) / 256;
+        float un[PER];
+#pragma unroll
+        for (int q = 0; q < PER; ++q) {
+            const int e = tid + q * 256;
+            un[q] = 0.f;
+            if (e < m * m) {
+                const int i = e / m, j = e - i * m;
+                float acc = 0.f;
+                for (int k = 0; k < m; ++k) acc = fmaf(U[i * P + k], S[k * P + j], acc);
+                un[q] = fmaf(-0.5f, acc, U[i * P + j]);
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int q = 0; q < PER; ++q) {
+            const int e = tid + q * 256;
+            if (e < m * m) U[(e / m) * P + (e % m)] = un[q];
+        }
+    }
     __syncthreads();
     // eigenvalues as Rayleigh quotients of the tridiagonal block (second-order accurate in the vector error)
     if (tid < nl) {
@@ -344,52 +375,55 @@ dc_vec_kernel(const DcMat* mats, const DcMerge* merges, const DcState* states) {
     for (int i = lane; i < K; i += 32) urow[i] = (zh[i] / urow[i]) * inv;
 }
 
-// final ascending position of the K roots (q < K) and of the deflated values (q >= K); roots first on ties
-__global__ void __launch_bounds__(1024)
+// final ascending position of the K roots (q < K) and of the deflated values (q >= K); roots first on ties.
+// grid (ceil(nm / 256), merges)
+__global__ void __launch_bounds__(256)
 dc_rank_kernel(const DcMat* mats, const DcMerge* merges, const DcState* states, int out, int nmax) {
     extern __shared__ float smem[];
-    const DcMerge mg = merges[blockIdx.x];
+    const DcMerge mg = merges[blockIdx.y];
+    const int nm = mg.n1 + mg.n2;
+    if ((int)blockIdx.x * 256 >= nm) return;
     const DcMat mt = mats[mg.mat];
-    const int nm = mg.n1 + mg.n2, off = mg.off, K = states[blockIdx.x].K, tid = threadIdx.x;
+    const int off = mg.off, K = states[blockIdx.y].K, tid = threadIdx.x;
     float* sv = smem;                                      // [0,K): roots, [K,nm): deflated values
     for (int q = tid; q < nm; q += blockDim.x) sv[q] = q < K ? mt.lam[off + q] : mt.vals[off + q];
     __syncthreads();
-    for (int q = tid; q < nm; q += blockDim.x) {
-        const float v = sv[q];
-        int rk;
-        if (q < K) {
-            rk = q;
-            for (int p = K; p < nm; ++p) rk += sv[p] < v;
-        } else {
-            int lo = 0, hi = K;
-            while (lo < hi) { const int mid = (lo + hi) >> 1; if (sv[mid] <= v) lo = mid + 1; else hi = mid; }
-            rk = lo;
-            for (int p = K; p < nm; ++p) rk += (sv[p] < v) || (sv[p] == v && p < q);
-        }
-        mt.rnk[off + q] = rk;
-        mt.dcur[out][off + rk] = v;
+    const int q = blockIdx.x * 256 + tid;
+    if (q >= nm) return;
+    const float v = sv[q];
+    int rk;
+    if (q < K) {
+        rk = q;
+        for (int p = K; p < nm; ++p) rk += sv[p] < v;
+    } else {
+        int lo = 0, hi = K;
+        while (lo < hi) { const int mid = (lo + hi) >> 1; if (sv[mid] <= v) lo = mid + 1; else hi = mid; }
+        rk = lo;
+        for (int p = K; p < nm; ++p) rk += (sv[p] < v) || (sv[p] == v && p < q);
     }
+    mt.rnk[off + q] = rk;
+    mt.dcur[out][off + rk] = v;
 }
 
-
 // One 128x128 output tile  sum_{k in [kbeg,kend)} A(m0+., k) B(n0+., k), handed element-wise to epi(m, n, value)
-// (local indices; lanes walk n).  TC: tcgen05 3xTF32 core (FLUSH bounds the in-TMEM chain for long K);
-// !TC: exact-fp32 SIMT core (KFACB_GEMM_SIMT=1, A/B accuracy comparisons).
-template <bool TC, bool FLUSH, class LA, class LB, class Epi>
-__device__ __forceinline__ void tile_product(const LA& la, const LB& lb, int m0, int n0, int kbeg, int kend,
+// (local indices; lanes walk n).  tc: the high-precision tcgen05 3xTF32 core (separate accumulators for the main and
+// the correction terms, main accumulator flushed to fp32 registers every k-slab pair -- tc_gemm.cuh);
+// !tc: exact-fp32 SIMT core (small matrices; everything with KFACB_GEMM_SIMT=1 for A/B accuracy comparisons).
+template <class LA, class LB, class Epi>
+__device__ __forceinline__ void tile_product(bool tc, const LA& la, const LB& lb, int m0, int n0, int kbeg, int kend,
                                              bool same_operand, const Epi& epi) {
-    if constexpr (TC) {
-        extern __shared__ __align__(128) unsigned char dsm_raw[];
+    extern __shared__ __align__(128) unsigned char dsm_raw[];
+    if (tc) {
         __shared__ __align__(8) uint64_t mbar;
         __shared__ uint32_t tmem_slot;
         tcg::Ctx c;
-        tcg::setup(c, dsm_raw, &mbar, &tmem_slot);
-        tcg::mainloop<FLUSH>(la, lb, m0, n0, kbeg, kend, same_operand, c);
-        const float* d = tcg::drain<FLUSH>(c, kend > kbeg);
+        tcg::setup_hp(c, dsm_raw, &mbar, &tmem_slot);           // two-accumulator, frequently flushed core (tc_gemm.cuh)
+        tcg::mainloop_hp(la, lb, m0, n0, kbeg, kend, same_operand, c);
+        const float* d = tcg::drain_hp(c, kend > kbeg);
         for (int e = threadIdx.x; e < TILE * TILE; e += tcg::THREADS) epi(e >> 7, e & 127, d[(e >> 7) * tcg::DPITCH + (e & 127)]);
-        tcg::teardown(c);
+        tcg::teardown_hp(c);
     } else {
-        __shared__ GemmSmem sm;
+        GemmSmem& sm = *reinterpret_cast<GemmSmem*>(dsm_raw);
         float acc[8][8];
 #pragma unroll
         for (int i = 0; i < 8; ++i)
@@ -402,6 +436,12 @@ __device__ __forceinline__ void tile_product(const LA& la, const LB& lb, int m0,
             for (int j = 0; j < 8; ++j) epi(frag_row(i), frag_col(j), acc[i][j]);
     }
 }
+static_assert(sizeof(GemmSmem) <= tcg::SMEM, "the SIMT core runs in the tensor-core core's dynamic shared memory");
+// Matrices up to this size run their GEMM-shaped stages on the exact-fp32 SIMT core: their flops are negligible
+// (sum n^3 over them is < 3 % of a ResNet-50 step) and the small, tightly clustered factors (conv1: n = 147 with
+// 4e5 samples) are where the preconditioned gradient is most sensitive to the orthogonality of Q.
+constexpr int SIMT_MAX_N = 640;
+__device__ __forceinline__ bool use_tc_for(int n, int force) { return force == 0 ? n > SIMT_MAX_N : force > 0; }
 static_assert(tcg::THREADS == GEMM_THREADS, "the tile kernels run either core with the same block size");
 
 // ---- GEMM-shaped kernels ----
@@ -432,9 +472,8 @@ struct LdZsrc {                                            // B(n = component c,
     }
 };
 
-template <bool TC>
 __global__ void __launch_bounds__(tcg::THREADS)
-dc_gemm_kernel(const DcMat* mats, const DcMerge* merges, const DcState* states, const Tile* tiles, int in) {
+dc_gemm_kernel(const DcMat* mats, const DcMerge* merges, const DcState* states, const Tile* tiles, int in, int force) {
     const Tile tl = tiles[blockIdx.x];                     // a = merge (within the level), b = tile m, c = tile n
     const int K = states[tl.a].K;
     if (tl.b * TILE >= K) return;
@@ -447,7 +486,7 @@ dc_gemm_kernel(const DcMat* mats, const DcMerge* merges, const DcState* states, 
     float* Zout = mt.Z[in ^ 1];
     const int* rnk = mt.rnk + off;
     const long ldz = mt.ldz;
-    tile_product<TC, true>(la, lb, m0, n0, 0, K, false, [=](int m, int n, float v) {
+    tile_product(use_tc_for(mt.n, force), la, lb, m0, n0, 0, K, false, [=](int m, int n, float v) {
         if (m0 + m < K && n0 + n < nm) Zout[(size_t)(off + rnk[m0 + m]) * ldz + off + n0 + n] = v;
     });
 }
@@ -590,9 +629,8 @@ bt_tinv_kernel(const DcMat* mats, const Tile* tiles) {
 }
 
 // Ypart[ks] = Zt[:, chunk ks] V_p[:, chunk ks]^T; tiles: a = matrix, b = tile m, c = chunk, d = panel
-template <bool TC>
 __global__ void __launch_bounds__(tcg::THREADS)
-bt_y_kernel(const DcMat* mats, const Tile* tiles) {
+bt_y_kernel(const DcMat* mats, const Tile* tiles, int force) {
     const Tile tl = tiles[blockIdx.x];
     const DcMat mt = mats[tl.a];
     const int jb = tl.d * PB, kp = min(PB, mt.n - 1 - jb);
@@ -601,7 +639,7 @@ bt_y_kernel(const DcMat* mats, const Tile* tiles) {
     LdVt lb{mt.T + (size_t)jb * mt.ldz, mt.ldz, jb, kp, mt.n};
     const int m0 = tl.b * TILE, n = mt.n;
     float* Y = mt.Ypart + (size_t)tl.c * mt.n * PB;
-    tile_product<TC, false>(la, lb, m0, 0, kbeg, kend, false, [=](int m, int r, float v) {
+    tile_product(use_tc_for(mt.n, force), la, lb, m0, 0, kbeg, kend, false, [=](int m, int r, float v) {
         if (m0 + m < n) Y[(size_t)(m0 + m) * PB + r] = v;
     });
 }
@@ -613,24 +651,22 @@ struct LdTb {
     __device__ __forceinline__ float operator()(int mn, int k) const { return __ldg(Tb + mn * PB + k); }
     __device__ __forceinline__ float4 quad(int mn, int k) const { return __ldg(reinterpret_cast<const float4*>(Tb + mn * PB + k)); }
 };
-template <bool TC>
 __global__ void __launch_bounds__(tcg::THREADS)
-bt_yt_kernel(const DcMat* mats, const Tile* tiles) {
+bt_yt_kernel(const DcMat* mats, const Tile* tiles, int force) {
     const Tile tl = tiles[blockIdx.x];
     const DcMat mt = mats[tl.a];
     LdYsum la{mt.Ypart, mt.n, tl.c};
     LdTb lb{mt.Tb + (size_t)tl.d * PB * PB};
     const int m0 = tl.b * TILE, n = mt.n;
     float* Y2 = mt.Y2;
-    tile_product<TC, false>(la, lb, m0, 0, 0, PB, false, [=](int m, int r, float v) {
+    tile_product(use_tc_for(mt.n, force), la, lb, m0, 0, 0, PB, false, [=](int m, int r, float v) {
         if (m0 + m < n) Y2[(size_t)(m0 + m) * PB + r] = v;
     });
 }
 
 // Zt[:, jb + 128 tn ..] -= Y2 V_p; tiles: a = matrix, b = tile m, c = tile n, d = panel
-template <bool TC>
 __global__ void __launch_bounds__(tcg::THREADS)
-bt_upd_kernel(const DcMat* mats, const Tile* tiles) {
+bt_upd_kernel(const DcMat* mats, const Tile* tiles, int force) {
     const Tile tl = tiles[blockIdx.x];
     const DcMat mt = mats[tl.a];
     const int jb = tl.d * PB, kp = min(PB, mt.n - 1 - jb);
@@ -639,7 +675,7 @@ bt_upd_kernel(const DcMat* mats, const Tile* tiles) {
     const int m0 = tl.b * TILE, n0 = tl.c * TILE, n = mt.n;
     float* Z = mt.Z[mt.fin];
     const long ldz = mt.ldz;
-    tile_product<TC, false>(la, lb, m0, n0, 0, PB, false, [=](int m, int c, float v) {
+    tile_product(use_tc_for(mt.n, force), la, lb, m0, n0, 0, PB, false, [=](int m, int c, float v) {
         const int cc = jb + n0 + c;
         if (m0 + m < n && cc < n) Z[(size_t)(m0 + m) * ldz + cc] -= v;
     });
@@ -953,7 +989,9 @@ int eigh_tdc_run(const int32_t* n, const int* idx, int nb, const float* const* M
     const Tile* d_yt = reinterpret_cast<const Tile*>(tb + pl.t_yt);
     const Tile* d_upd = reinterpret_cast<const Tile*>(tb + pl.t_upd);
 
-    const bool tc = use_tc_gemm();
+    // GEMM core per matrix: 0 = by size (SIMT up to SIMT_MAX_N), -1 = SIMT everywhere (KFACB_GEMM_SIMT=1), +1 = tensor cores everywhere
+    static int force = -2;
+    if (force == -2) { const char* e = getenv("KFACB_TDC_TC"); force = !use_tc_gemm() ? -1 : ((e && *e) ? (atoi(e) > 0 ? 1 : -1) : 0); }
     static int dbg = -1;                        // KFACB_TDC_DEBUG=1: skip the back-transformation (Q = eigenvectors of T)
     if (dbg < 0) { const char* e = getenv("KFACB_TDC_DEBUG"); dbg = (e && *e) ? atoi(e) : 0; }
     StageEvents* sev = stage_events();
@@ -987,10 +1025,10 @@ int eigh_tdc_run(const int32_t* n, const int* idx, int nb, const float* const* M
         KFACB_CHECK_CUDA(cudaFuncSetAttribute(dc_prep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * trd::MAXN * 4));
         KFACB_CHECK_CUDA(cudaFuncSetAttribute(dc_secular_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * trd::MAXN * 4));
         KFACB_CHECK_CUDA(cudaFuncSetAttribute(dc_rank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, trd::MAXN * 4));
-        KFACB_CHECK_CUDA(cudaFuncSetAttribute(dc_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tcg::SMEM));
-        KFACB_CHECK_CUDA(cudaFuncSetAttribute(bt_y_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tcg::SMEM));
-        KFACB_CHECK_CUDA(cudaFuncSetAttribute(bt_yt_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tcg::SMEM));
-        KFACB_CHECK_CUDA(cudaFuncSetAttribute(bt_upd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tcg::SMEM));
+        KFACB_CHECK_CUDA(cudaFuncSetAttribute(dc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tcg::SMEM));
+        KFACB_CHECK_CUDA(cudaFuncSetAttribute(bt_y_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tcg::SMEM));
+        KFACB_CHECK_CUDA(cudaFuncSetAttribute(bt_yt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tcg::SMEM));
+        KFACB_CHECK_CUDA(cudaFuncSetAttribute(bt_upd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tcg::SMEM));
         KFACB_CHECK_CUDA(cudaFuncSetAttribute(bt_tinv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * PB * TP * 4));
         if (dev >= 0 && dev < 64) attr_done[dev] = true;
     }
@@ -1014,12 +1052,10 @@ int eigh_tdc_run(const int32_t* n, const int* idx, int nb, const float* const* M
         dc_secular_kernel<<<dim3(cdiv(nmx, 8), nmg), 256, 2 * (size_t)nmx * sizeof(float), st>>>(d_mats, mg, sts, nmx);
         dc_zhat_kernel<<<dim3(cdiv(nmx, 32), nmg), 1024, 0, st>>>(d_mats, mg, sts);
         dc_vec_kernel<<<dim3(cdiv(nmx, 8), nmg), 256, 0, st>>>(d_mats, mg, sts);
-        dc_rank_kernel<<<nmg, 1024, (size_t)nmx * sizeof(float), st>>>(d_mats, mg, sts, out, nmx);
+        dc_rank_kernel<<<dim3(cdiv(nmx, 256), nmg), 256, (size_t)nmx * sizeof(float), st>>>(d_mats, mg, sts, out, nmx);
         const int ngt = pl.gemm_off[l + 1] - pl.gemm_off[l];
-        if (ngt > 0) {
-            if (tc) dc_gemm_kernel<true><<<ngt, tcg::THREADS, tcg::SMEM, st>>>(d_mats, mg, sts, d_gemm + pl.gemm_off[l], in);
-            else dc_gemm_kernel<false><<<ngt, tcg::THREADS, 0, st>>>(d_mats, mg, sts, d_gemm + pl.gemm_off[l], in);
-        }
+        if (ngt > 0)
+            dc_gemm_kernel<<<ngt, tcg::THREADS, tcg::SMEM, st>>>(d_mats, mg, sts, d_gemm + pl.gemm_off[l], in, force);
         dc_copy_kernel<<<dim3(cdiv(nmx, 8), nmg), 256, 0, st>>>(d_mats, mg, sts, in);
         count_launch(8);
         KFACB_CHECK_LAUNCH();
@@ -1035,15 +1071,9 @@ int eigh_tdc_run(const int32_t* n, const int* idx, int nb, const float* const* M
         for (int it = 0; it < pl.max_panels; ++it) {
             const int ny = pl.y_off[it + 1] - pl.y_off[it], nyt = pl.yt_off[it + 1] - pl.yt_off[it], nu = pl.upd_off[it + 1] - pl.upd_off[it];
             if (ny == 0) continue;
-            if (tc) {
-                bt_y_kernel<true><<<ny, tcg::THREADS, tcg::SMEM, st>>>(d_mats, d_y + pl.y_off[it]);
-                bt_yt_kernel<true><<<nyt, tcg::THREADS, tcg::SMEM, st>>>(d_mats, d_yt + pl.yt_off[it]);
-                bt_upd_kernel<true><<<nu, tcg::THREADS, tcg::SMEM, st>>>(d_mats, d_upd + pl.upd_off[it]);
-            } else {
-                bt_y_kernel<false><<<ny, tcg::THREADS, 0, st>>>(d_mats, d_y + pl.y_off[it]);
-                bt_yt_kernel<false><<<nyt, tcg::THREADS, 0, st>>>(d_mats, d_yt + pl.yt_off[it]);
-                bt_upd_kernel<false><<<nu, tcg::THREADS, 0, st>>>(d_mats, d_upd + pl.upd_off[it]);
-            }
+            bt_y_kernel<<<ny, tcg::THREADS, tcg::SMEM, st>>>(d_mats, d_y + pl.y_off[it], force);
+            bt_yt_kernel<<<nyt, tcg::THREADS, tcg::SMEM, st>>>(d_mats, d_yt + pl.yt_off[it], force);
+            bt_upd_kernel<<<nu, tcg::THREADS, tcg::SMEM, st>>>(d_mats, d_upd + pl.upd_off[it], force);
             count_launch(2);
             KFACB_CHECK_LAUNCH();
         }

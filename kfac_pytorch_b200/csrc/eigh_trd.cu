@@ -22,6 +22,7 @@
 //     operand layout the tensor-core back-transformation (eigh_dc.cu) wants.
 // The formulas are pinned by tools/eigh_trd_dc_model.py (same phases in numpy).
 #include <stdlib.h>
+#include <type_traits>
 #include "eigh_trd.cuh"
 
 namespace kfacb {
@@ -61,12 +62,21 @@ __device__ __forceinline__ int first_own(int r0, int rank, int team) {
     return r0 + o;
 }
 
-// Team-wide sums of the partial sums of the last product pass: quantity k lives in part[k * TS + rank]; one warp
-// adds the team's slots of a quantity (coalesced, fixed order: identical bits on every CTA).  Only the kc live panel
-// columns of s = W^T v and t = V^T v are read.  The loads of a warp's quantities are issued together.
+// Team-wide sums of the partial sums of the last product pass + what finishing column `kc` of W needs.
+// Quantity k lives in part[k * TS + rank]; one warp adds the team's slots of a quantity (coalesced, fixed order:
+// identical bits on every CTA); only the kc live panel columns of s = W^T v (q[0..)) and t = V^T v (q[32..)) are
+// read; every load of a warp is issued before the first reduction.  Then warp 0 forms
+// cw = tau^2 (v.y - 2 s.t) / 2 and, with want_row, finishes W[row_j][kc] redundantly (every CTA needs row j of the
+// panels) and stages rows j of V and W -- its loads of row j were issued together with the partial sums.
 // All threads; ends with a barrier.
-__device__ __forceinline__ void reduce_st(const Job& jb, Smem& sm, int kc) {
+__device__ __forceinline__ void reduce_and_prologue(const Job& jb, Smem& sm, int kc, int row_j, bool want_row) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float vj = 0.f, wj = 0.f, yj = 0.f;
+    if (warp == 0 && want_row) {
+        vj = lane <= kc ? __ldcg(jb.Vp + (size_t)row_j * NB + lane) : 0.f;
+        wj = lane < kc ? __ldcg(jb.Wp + (size_t)row_j * NB + lane) : 0.f;
+        yj = __ldcg(jb.y + row_j);
+    }
     constexpr int PER = (65 + NWARP - 1) / NWARP;               // quantities per warp
     float a[PER];
 #pragma unroll
@@ -74,8 +84,13 @@ __device__ __forceinline__ void reduce_st(const Job& jb, Smem& sm, int kc) {
         const int k = warp + NWARP * u;
         a[u] = 0.f;
         const bool live = k < 65 && (k == 64 || (k & 31) < kc);
-        if (live)
-            for (int r = lane; r < jb.team; r += 32) a[u] += __ldcg(jb.part + k * TS + r);
+        if (live) {
+#pragma unroll
+            for (int it = 0; it < TS / 32; ++it) {               // fixed trip count: every load of the warp is in flight at once
+                const int r = lane + 32 * it;
+                if (r < jb.team) a[u] += __ldcg(jb.part + k * TS + r);
+            }
+        }
     }
 #pragma unroll
     for (int u = 0; u < PER; ++u) {
@@ -84,29 +99,22 @@ __device__ __forceinline__ void reduce_st(const Job& jb, Smem& sm, int kc) {
         if (lane == 0 && k < 65) sm.q[k] = t;
     }
     __syncthreads();
-}
-
-// What finishing column `kc` of W needs, from the reduced sums s = W^T v = q[0..), t = V^T v = q[32..):
-// cw = tau^2 (v.y - 2 s.t) / 2.  With want_row it also finishes W[row_j][kc] redundantly (every CTA needs row j of
-// the panels) and stages rows j of V and W.  Warp 0 only; followed by __syncthreads.
-__device__ __forceinline__ void finish_prologue(const Job& jb, Smem& sm, int kc, int row_j, bool want_row) {
-    const int lane = threadIdx.x & 31;
-    const float s = sm.q[lane], t = sm.q[32 + lane], vy = sm.q[64];
-    const float st = warp_sum(lane < kc ? s * t : 0.f);
-    const float tau = sm.tau;
-    const float cw = 0.5f * tau * tau * (vy - 2.f * st);
-    if (lane == 0) sm.cw = cw;
-    if (want_row) {
-        const float vj = lane <= kc ? __ldcg(jb.Vp + (size_t)row_j * NB + lane) : 0.f;
-        float wj = lane < kc ? __ldcg(jb.Wp + (size_t)row_j * NB + lane) : 0.f;
-        const float dot = warp_sum(lane < kc ? vj * s + wj * t : 0.f);
-        const float yj = __ldcg(jb.y + row_j);
-        const float vlast = __shfl_sync(0xffffffffu, vj, kc);
-        const float wnew = tau * (yj - dot) - cw * vlast;
-        if (lane == kc) wj = wnew;
-        sm.rowV[lane] = vj;
-        sm.rowW[lane] = wj;
+    if (warp == 0) {
+        const float s = sm.q[lane], t = sm.q[32 + lane], vy = sm.q[64];
+        const float st = warp_sum(lane < kc ? s * t : 0.f);
+        const float tau = sm.tau;
+        const float cw = 0.5f * tau * tau * (vy - 2.f * st);
+        if (lane == 0) sm.cw = cw;
+        if (want_row) {
+            const float dot = warp_sum(lane < kc ? vj * s + wj * t : 0.f);
+            const float vlast = __shfl_sync(0xffffffffu, vj, kc);
+            const float wnew = tau * (yj - dot) - cw * vlast;
+            if (lane == kc) wj = wnew;
+            sm.rowV[lane] = vj;
+            sm.rowW[lane] = wj;
+        }
     }
+    __syncthreads();
 }
 
 // A[R0.., R0..] -= V W^T + W V^T over the first kc panel columns; tiles of 128x128 dealt to the team.
@@ -201,30 +209,56 @@ __device__ void run_job(const Job& jb, int rank, Smem& sm) {
         const int jp = j - j0;
         // ---------------- phase A: finish w_{j-1} (rows >= j), form column j and |x|^2 ----------------
         if (jp > 0) {
-            reduce_st(jb, sm, jp - 1);
-            if (warp == 0) finish_prologue(jb, sm, jp - 1, j, true);
-            __syncthreads();
+            reduce_and_prologue(jb, sm, jp - 1, j, true);
         }
         TRD_TICK(0);
         {
             const float tau_p = sm.tau, cw = sm.cw;
             float nrm = 0.f;
-            for (int i = first_own(j, rank, team) + team * warp; i < n; i += team * NWARP) {
-                float vk = lane < jp ? __ldcg(jb.Vp + (size_t)i * NB + lane) : 0.f;       // (all four loads in flight together)
-                float wk = lane < jp - 1 ? __ldcg(jb.Wp + (size_t)i * NB + lane) : 0.f;
-                const float yi = jp > 0 ? __ldcg(jb.y + i) : 0.f;
-                const float tji = __ldcg(jb.T + (size_t)j * ldt + i);
-                if (jp > 0) {
-                    const float dot = warp_sum(lane < jp - 1 ? vk * sm.q[lane] + wk * sm.q[32 + lane] : 0.f);
-                    const float vlast = __shfl_sync(0xffffffffu, vk, jp - 1);
-                    const float wnew = tau_p * (yi - dot) - cw * vlast;
-                    if (lane == jp - 1) { wk = wnew; jb.Wp[(size_t)i * NB + lane] = wnew; }
+            // AR rows per warp iteration: their loads are all issued before the first dependent reduction
+            constexpr int AR = 4;
+            for (int i0 = first_own(j, rank, team) + team * warp; i0 < n; i0 += team * NWARP * AR) {
+                float vk[AR], wk[AR], yi[AR], tji[AR];
+#pragma unroll
+                for (int u = 0; u < AR; ++u) {
+                    const int i = i0 + u * team * NWARP;
+                    const bool ok = i < n;
+                    vk[u] = (ok && lane < jp) ? __ldcg(jb.Vp + (size_t)i * NB + lane) : 0.f;
+                    wk[u] = (ok && lane < jp - 1) ? __ldcg(jb.Wp + (size_t)i * NB + lane) : 0.f;
+                    yi[u] = (ok && jp > 0) ? __ldcg(jb.y + i) : 0.f;
+                    tji[u] = ok ? __ldcg(jb.T + (size_t)j * ldt + i) : 0.f;
                 }
-                const float corr = warp_sum(lane < jp ? vk * sm.rowW[lane] + wk * sm.rowV[lane] : 0.f);
-                const float xi = tji - corr;
-                if (lane == 0) {
-                    if (i == j) jb.d[j] = xi;
-                    else { jb.x[i] = xi; if (i >= j + 2) nrm = fmaf(xi, xi, nrm); }
+                if (jp > 0) {                                       // the AR reductions are independent: interleaved by the unrolling
+                    float dot[AR];
+#pragma unroll
+                    for (int u = 0; u < AR; ++u) dot[u] = lane < jp - 1 ? vk[u] * sm.q[lane] + wk[u] * sm.q[32 + lane] : 0.f;
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+                        for (int u = 0; u < AR; ++u) dot[u] += __shfl_xor_sync(0xffffffffu, dot[u], o);
+#pragma unroll
+                    for (int u = 0; u < AR; ++u) {
+                        const int i = i0 + u * team * NWARP;
+                        const float vlast = __shfl_sync(0xffffffffu, vk[u], jp - 1);
+                        const float wnew = tau_p * (yi[u] - dot[u]) - cw * vlast;
+                        if (lane == jp - 1 && i < n) { wk[u] = wnew; jb.Wp[(size_t)i * NB + lane] = wnew; }
+                    }
+                }
+                float corr[AR];
+#pragma unroll
+                for (int u = 0; u < AR; ++u) corr[u] = lane < jp ? vk[u] * sm.rowW[lane] + wk[u] * sm.rowV[lane] : 0.f;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+                    for (int u = 0; u < AR; ++u) corr[u] += __shfl_xor_sync(0xffffffffu, corr[u], o);
+#pragma unroll
+                for (int u = 0; u < AR; ++u) {
+                    const int i = i0 + u * team * NWARP;
+                    const float xi = tji[u] - corr[u];
+                    if (lane == 0 && i < n) {
+                        if (i == j) jb.d[j] = xi;
+                        else { jb.x[i] = xi; if (i >= j + 2) nrm = fmaf(xi, xi, nrm); }
+                    }
                 }
             }
             if (lane == 0) sm.red[0][warp][0] = nrm;
@@ -249,7 +283,11 @@ __device__ void run_job(const Job& jb, int rank, Smem& sm) {
         }
         if (warp == 0) {
             float s2 = 0.f;
-            for (int r = lane; r < team; r += 32) s2 += __ldcg(jb.part + 65 * TS + r);
+#pragma unroll
+            for (int it = 0; it < TS / 32; ++it) {
+                const int r = lane + 32 * it;
+                if (r < team) s2 += __ldcg(jb.part + 65 * TS + r);
+            }
             s2 = warp_sum(s2);
             const float alpha = __ldcg(jb.x + j + 1);
             float beta, tau, scale;
@@ -278,36 +316,61 @@ __device__ void run_job(const Job& jb, int rank, Smem& sm) {
         {
             float acc_s = 0.f, acc_t = 0.f, acc_vy = 0.f;
             const int q_beg = c_al >> 2, q_end = ldt >> 2;
-            for (int i = first_own(j + 1, rank, team) + team * warp; i < n; i += team * NWARP) {
-                const float4* row = reinterpret_cast<const float4*>(jb.T + (size_t)i * ldt);
-                // panel rows of this matrix row: issued before the long product, consumed after it
-                const float wpi = lane < jp ? __ldcg(jb.Wp + (size_t)i * NB + lane) : 0.f;
-                const float vpi = lane < jp ? __ldcg(jb.Vp + (size_t)i * NB + lane) : 0.f;
-                float a0 = 0.f, a1 = 0.f;
-                for (int q = q_beg + lane; q < q_end; q += 256) {       // 8 predicated 16-byte loads in flight per lane
-                    float4 m[8];
+            // RB rows x LD predicated 16-byte loads per lane in flight (RB * LD = 8), chosen by the row length:
+            // long rows stream one row at a time, short rows (small matrices, the tail of every matrix) go RB at once
+            const int qlen = q_end - q_beg;
+            auto rows_product = [&](auto rb_tag, auto ld_tag) {
+                constexpr int RB = decltype(rb_tag)::value, LD = decltype(ld_tag)::value;
+                for (int i0 = first_own(j + 1, rank, team) + team * warp; i0 < n; i0 += team * NWARP * RB) {
+                    float wpi[RB], vpi[RB], acc[RB];
 #pragma unroll
-                    for (int u = 0; u < 8; ++u)
-                        m[u] = (q + 32 * u < q_end) ? __ldcg(row + q + 32 * u) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    for (int u = 0; u < RB; ++u) {
+                        const int i = i0 + u * team * NWARP;
+                        wpi[u] = (i < n && lane < jp) ? __ldcg(jb.Wp + (size_t)i * NB + lane) : 0.f;
+                        vpi[u] = (i < n && lane < jp) ? __ldcg(jb.Vp + (size_t)i * NB + lane) : 0.f;
+                        acc[u] = 0.f;
+                    }
+                    for (int q = q_beg + lane; q < q_end; q += 32 * LD) {
+                        float4 m[RB][LD];
 #pragma unroll
-                    for (int u = 0; u < 8; ++u) {
-                        const int qq = (q + 32 * u < q_end) ? q + 32 * u : q;
-                        const float4 vv = *reinterpret_cast<const float4*>(&sm.v[4 * qq]);
-                        const float t = fmaf(m[u].x, vv.x, fmaf(m[u].y, vv.y, fmaf(m[u].z, vv.z, m[u].w * vv.w)));
-                        if (u & 1) a1 += t; else a0 += t;
+                        for (int u = 0; u < RB; ++u) {
+                            const int i = i0 + u * team * NWARP;
+                            const float4* row = reinterpret_cast<const float4*>(jb.T + (size_t)(i < n ? i : i0) * ldt);
+#pragma unroll
+                            for (int l = 0; l < LD; ++l)
+                                m[u][l] = (i < n && q + 32 * l < q_end) ? __ldcg(row + q + 32 * l) : make_float4(0.f, 0.f, 0.f, 0.f);
+                        }
+#pragma unroll
+                        for (int l = 0; l < LD; ++l) {
+                            const int qq = (q + 32 * l < q_end) ? q + 32 * l : q;
+                            const float4 vv = *reinterpret_cast<const float4*>(&sm.v[4 * qq]);
+#pragma unroll
+                            for (int u = 0; u < RB; ++u)
+                                acc[u] += fmaf(m[u][l].x, vv.x, fmaf(m[u][l].y, vv.y, fmaf(m[u][l].z, vv.z, m[u][l].w * vv.w)));
+                        }
+                    }
+#pragma unroll
+                    for (int u = 0; u < RB; ++u) {
+                        const int i = i0 + u * team * NWARP;
+                        if (i >= n) break;
+                        const float yi = warp_sum(acc[u]);
+                        const float vi = sm.v[i];
+                        acc_s = fmaf(wpi[u], vi, acc_s);
+                        acc_t = fmaf(vpi[u], vi, acc_t);
+                        if (lane == 0) {
+                            jb.y[i] = yi;
+                            acc_vy = fmaf(vi, yi, acc_vy);
+                            jb.Vp[(size_t)i * NB + jp] = vi;
+                            jb.T[(size_t)j * ldt + i] = vi;
+                        }
                     }
                 }
-                const float yi = warp_sum(a0 + a1);
-                const float vi = sm.v[i];
-                acc_s = fmaf(wpi, vi, acc_s);
-                acc_t = fmaf(vpi, vi, acc_t);
-                if (lane == 0) {
-                    jb.y[i] = yi;
-                    acc_vy = fmaf(vi, yi, acc_vy);
-                    jb.Vp[(size_t)i * NB + jp] = vi;
-                    jb.T[(size_t)j * ldt + i] = vi;
-                }
-            }
+            };
+            using I1 = std::integral_constant<int, 1>; using I2 = std::integral_constant<int, 2>;
+            using I4 = std::integral_constant<int, 4>; using I8 = std::integral_constant<int, 8>;
+            if (qlen > 128) rows_product(I1{}, I8{});
+            else if (qlen > 32) rows_product(I2{}, I4{});
+            else rows_product(I8{}, I1{});
             TRD_TICK(4);
             sm.red[0][warp][lane] = acc_s;
             sm.red[1][warp][lane] = acc_t;
@@ -326,9 +389,7 @@ __device__ void run_job(const Job& jb, int rank, Smem& sm) {
         TRD_TICK(6);
         // ---------------- panel end: finish w_j (rows > j), rank-2k update of the trailing square ----------------
         if (jp == NB - 1 || j == n - 2) {
-            reduce_st(jb, sm, jp);
-            if (warp == 0) finish_prologue(jb, sm, jp, 0, false);
-            __syncthreads();
+            reduce_and_prologue(jb, sm, jp, 0, false);
             const float tau_p = sm.tau, cw = sm.cw;
             for (int i = first_own(j + 1, rank, team) + team * warp; i < n; i += team * NWARP) {
                 const float vk = lane <= jp ? __ldcg(jb.Vp + (size_t)i * NB + lane) : 0.f;
@@ -402,13 +463,17 @@ __global__ void trd_copy_kernel(const Job* jobs, const float* const* src) {
 // ---------------------------------------------------------------------------
 // host: team sizes and the per-CTA schedule
 // ---------------------------------------------------------------------------
+// Cost model of one job on a team (seconds), calibrated on B200 with KFACB_TRD_PROF / KFACB_TRD_TEAM
+// (profiles/r02_trd_calibration.txt): per column two team barriers (~1.6 us each) + the latency-bound short phases;
+// rows handled one warp-batch after the other (matters for small teams); the product streams 4 m^2 bytes per
+// column at ~60 GB/s per SM up to the HBM / L2 ceiling; the rank-2k updates do 4/3 n^3 flops at ~150 GFLOP/s per SM.
 static double job_time(int n, int team) {
-    const double t_step = team > 1 ? 3.0e-6 : 1.5e-6;                 // two barriers + the short phases
-    double bw = 40e9 * team;                                          // streaming rate of a team (HBM share / SM)
-    if (bw > 5.2e12) bw = 5.2e12;
-    const double n3 = (double)n * n * n;
-    // product: 4 m^2 bytes per column = 4/3 n^3 bytes; rank-2k updates: 4/3 n^3 flops at ~0.2 TFLOP/s per SM (SIMT)
-    return n * t_step + (4.0 / 3.0) * n3 / bw + (4.0 / 3.0) * n3 / (0.2e12 * team);
+    const double t_fix = team > 1 ? 7.5e-6 : 4.5e-6;
+    double bw = 60e9 * team;
+    if (bw > 6.0e12) bw = 6.0e12;
+    const double n2 = (double)n * n, n3 = n2 * n;
+    const double t_rows = (n2 / 2.0) / (16.0 * team) * 0.75e-6;
+    return n * t_fix + t_rows + (4.0 / 3.0) * n3 / bw + (4.0 / 3.0) * n3 / (150e9 * team);
 }
 
 int plan_teams(const int* n, int njobs, int sms, int* team, int* cta_begin, int* entries) {

@@ -193,6 +193,109 @@ __device__ __forceinline__ float* drain(Ctx& c, bool has_data) {
     return d;
 }
 
+// ---------------------------------------------------------------------------
+// High-precision variant ("hp") for products whose error is amplified downstream (the orthogonal transformations
+// of the eigensolver).  Measured on B200: every tcgen05.mma accumulation into TMEM TRUNCATES at the accumulator's
+// ulp (~1 ulp of systematic loss per MMA), and a tiny addend (the lo*hi / hi*lo correction terms, 2^-11 of the
+// main term) is truncated at the BIG accumulator's ulp too.  A 60-MMA chain lost 4e-6 of orthogonality per GEMM.
+//   * two accumulators: TMEM columns [0,128) take hi*hi only, [128,256) take the two cross terms, so the cross
+//     terms are aligned to their own (small) magnitude; they are added once, in fp32 RN, at the drain;
+//   * the main accumulator is flushed into fp32 registers (RN adds) every HP_FLUSH_SLABS slab(s) = 4 MMAs, which
+//     also restarts the truncation at the magnitude of a 64-term partial sum instead of the running total.
+// Same MMA count and staging as the standard core; ~5e-7 per GEMM like an fp32 FMA chain.
+// ---------------------------------------------------------------------------
+constexpr int HP_FLUSH_SLABS = 1;
+
+__device__ __forceinline__ void setup_hp(Ctx& c, unsigned char* dsm, uint64_t* mbar, uint32_t* tmem_slot) {
+    if (threadIdx.x == 0) { tc::mbar_init(mbar, 1); tc::fence_mbar_init(); }
+    if ((threadIdx.x >> 5) == 0) tc::tmem_alloc<256>(tmem_slot);
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    c.dsm = dsm; c.mbar = mbar; c.tmem = *tmem_slot; c.slabs_done = 0; c.flushed = 0;
+}
+__device__ __forceinline__ void teardown_hp(Ctx& c) {
+    tc::tc_fence_before();
+    __syncthreads();
+    if ((threadIdx.x >> 5) == 0) tc::tmem_dealloc<256>(c.tmem);
+}
+
+template <class LA, class LB>
+__device__ __forceinline__ void mainloop_hp(const LA& la, const LB& lb, int m0, int n0, int kbeg, int kend,
+                                            bool same_operand, Ctx& c) {
+    unsigned char* a_hi = c.dsm;
+    unsigned char* a_lo = c.dsm + PART;
+    unsigned char* b_hi = same_operand ? a_hi : c.dsm + 2 * PART;
+    unsigned char* b_lo = same_operand ? a_lo : c.dsm + 3 * PART;
+    float4 ra[4], rb[4];
+    const int nslab = (kend - kbeg + BKS - 1) / BKS;
+    if (nslab > 0) { fetch(la, m0, kbeg, ra); if (!same_operand) fetch(lb, n0, kbeg, rb); }
+    constexpr uint32_t idesc = tc::idesc_tf32(128, 128, 0, 0);
+    int since = 0;                                           // slabs in the main accumulator since the last flush
+    for (int s = 0; s < nslab; ++s) {
+        if (c.slabs_done > 0) tc::mbar_wait(c.mbar, (uint32_t)((c.slabs_done - 1) & 1));   // smem free, MMAs complete
+        if (since == HP_FLUSH_SLABS) { tc::tc_fence_after(); flush_add(c); since = 0; }
+        stage<LA>(a_hi, a_lo, ra);
+        if (!same_operand) stage<LB>(b_hi, b_lo, rb);
+        if (s + 1 < nslab) {
+            fetch(la, m0, kbeg + (s + 1) * BKS, ra);
+            if (!same_operand) fetch(lb, n0, kbeg + (s + 1) * BKS, rb);
+        }
+        tc::fence_async_smem();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            tc::tc_fence_after();
+            const uint32_t ah = tc::smem_u32(a_hi), al = tc::smem_u32(a_lo);
+            const uint32_t bh = tc::smem_u32(b_hi), bl = tc::smem_u32(b_lo);
+            const bool first_cross = c.slabs_done == 0;
+#pragma unroll
+            for (int j = 0; j < BKS / 8; ++j)                 // hi * hi -> main accumulator
+                tc::umma_tf32(c.tmem, tc::smem_desc(ah + 2 * j * LBO, LBO, SBO), tc::smem_desc(bh + 2 * j * LBO, LBO, SBO),
+                              idesc, !(since == 0 && j == 0));
+#pragma unroll
+            for (int j = 0; j < BKS / 8; ++j)                 // lo * hi -> cross accumulator
+                tc::umma_tf32(c.tmem + 128, tc::smem_desc(al + 2 * j * LBO, LBO, SBO), tc::smem_desc(bh + 2 * j * LBO, LBO, SBO),
+                              idesc, !(first_cross && j == 0));
+#pragma unroll
+            for (int j = 0; j < BKS / 8; ++j)                 // hi * lo -> cross accumulator
+                tc::umma_tf32(c.tmem + 128, tc::smem_desc(ah + 2 * j * LBO, LBO, SBO), tc::smem_desc(bl + 2 * j * LBO, LBO, SBO),
+                              idesc, true);
+            tc::umma_commit(c.mbar);
+        }
+        c.slabs_done += 1;
+        since += 1;
+    }
+    if (c.slabs_done > 0) tc::mbar_wait(c.mbar, (uint32_t)((c.slabs_done - 1) & 1));
+    tc::tc_fence_after();
+}
+
+// main (+ flushed registers) + cross -> shared memory float[128][DPITCH]
+__device__ __forceinline__ float* drain_hp(Ctx& c, bool has_data) {
+    float* d = reinterpret_cast<float*>(c.dsm);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m = 32 * (warp & 3) + lane;
+    const int cbase = (warp >> 2) * 64;
+    float v[32], x[32];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        if (has_data) {
+            const uint32_t ta = c.tmem + ((uint32_t)(32 * (warp & 3)) << 16) + cbase + 32 * h;
+            tc::tmem_ld32(ta, v);
+            tc::tmem_ld32(ta + 128, x);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = (c.flushed ? v[i] + c.acc[32 * h + i] : v[i]) + x[i];
+        } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = 0.f;
+        }
+#pragma unroll
+        for (int i = 0; i < 32; ++i) d[m * DPITCH + cbase + 32 * h + i] = v[i];
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    return d;
+}
+
 // generic GEMM: C(m, n) = epi(m, n, sum_k A(m,k) B(n,k)); grid (tiles_n, tiles_m)
 // FLUSH is chosen by the host from K: products with K <= 512 keep the chain short anyway and run the
 // register-lean variant (3 CTAs / SM).

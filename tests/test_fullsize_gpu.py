@@ -35,8 +35,9 @@ def test_eigh_resnet50_factor_sizes(eng, n, rows):
     assert (Q64.t() @ Q64 - torch.eye(n, device=DEV, dtype=torch.float64)).abs().max().item() < 1e-5
     rec = (Q64 * d64) @ Q64.t()
     assert (rec - A64).norm().item() <= 1e-4 * A64.norm().item()
-    if n == 4608:       # rank(x^T x) = 1568 < n: the 0.05 cluster of the identity part must come out flat
-        assert (d64[: n - rows] - 0.05).abs().max().item() < 2e-6
+    if n == 4608:       # rank(x^T x) = 1568 < n: the 0.05 cluster of the identity part must come out flat --
+        # to the backward error of an fp32 eigensolver, a few eps * ||A|| (||A|| ~ 7 here; LAPACK ssyevd: ~3e-6)
+        assert (d64[: n - rows] - 0.05).abs().max().item() < 1e-6 * d64.max().item()
     assert 1 <= int(sw.item()) <= 16
 
 
