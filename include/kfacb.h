@@ -116,8 +116,8 @@ int    kfacb_factor_update(const kfacb_layer_t* layers, int32_t count,
  * torch.linalg.eigh) = Q diag(d) Q^T with d ascending, eigenvectors in the COLUMNS
  * of Q[i] (row-major n x n), then d <- d * (d > eps_floor).  Eigenvectors are
  * defined up to sign / rotation inside degenerate clusters.
- *   n <= 128: two-sided cyclic Jacobi, one CTA per matrix, in shared memory.
- *   n  > 128: Householder tridiagonalisation of the whole batch in ONE persistent
+ *   n <= 64 : two-sided cyclic Jacobi, one CTA per matrix, in shared memory.
+ *   n  > 64 : Householder tridiagonalisation of the whole batch in ONE persistent
  *             kernel (teams of CTAs per matrix), divide and conquer on the
  *             tridiagonal matrices, block-reflector back-transformation on the
  *             tensor cores.  Fixed launch sequence: the call only ENQUEUES work (no
@@ -125,7 +125,7 @@ int    kfacb_factor_update(const kfacb_layer_t* layers, int32_t count,
  *             n <= 8192.  (KFACB_EIGH_ALGO=jacobi selects the round-1 block-Jacobi
  *             path, which does synchronise the host on its progress events.)
  * sweeps_out (device int32[count], may be NULL) receives the number of Jacobi
- * sweeps (n <= 128) or 1.
+ * sweeps (n <= 64) or 1.
  * ------------------------------------------------------------------------- */
 size_t kfacb_eigh_workspace_bytes(const int32_t* n, int32_t count);
 int    kfacb_eigh_batched(const int32_t* n, int32_t count,
@@ -135,7 +135,7 @@ int    kfacb_eigh_batched(const int32_t* n, int32_t count,
                           kfacb_stream_t stream);
 
 /* Scheduler introspection (no GPU needed): team_out[i] = CTAs that tridiagonalise matrix i on a device with
- * `sms` SMs (0 for n[i] <= 128); returns the number of CTAs of the persistent kernel, < 0 on bad arguments. */
+ * `sms` SMs (0 for n[i] <= 64); returns the number of CTAs of the persistent kernel, < 0 on bad arguments. */
 int    kfacb_eigh_plan_teams(const int32_t* n, int32_t count, int32_t sms, int32_t* team_out);
 
 /* Benchmark aid.  kfacb_eigh_batched records CUDA events on the caller's stream around its stages (asynchronous);

@@ -1097,9 +1097,13 @@ extern "C" int kfacb_eigh_last_profile(double* out8) {
 static size_t direct_tables_bytes(int n_direct) {
     return align_up(sizeof(DirectMat) * (size_t)(n_direct + 1), 256) + align_up(sizeof(int) * (size_t)(n_direct + 1), 256);
 }
+// In-shared-memory Jacobi up to this size; above, tridiagonalisation + divide and conquer.  (The Jacobi kernel handles
+// up to DIRECT_MAX_N = 128, but one 128-dim matrix keeps its single CTA busy for ~5 ms -- a serial stage in front
+// of every step -- while the other path does it in ~1 ms.)
+constexpr int TDC_DIRECT_N = 64;
 static int collect_blocked(const int32_t* n, int count, int* idx) {
     int nb = 0;
-    for (int i = 0; i < count; ++i) if (n[i] > DIRECT_MAX_N) idx[nb++] = i;
+    for (int i = 0; i < count; ++i) if (n[i] > TDC_DIRECT_N) idx[nb++] = i;
     return nb;
 }
 
@@ -1128,7 +1132,7 @@ extern "C" int kfacb_eigh_batched(const int32_t* n, int32_t count,
     cudaStream_t st = (cudaStream_t)stream;
     KFACB_REQUIRE(n && M && Q && d && count >= 0, "null argument");
     if (!use_block_jacobi()) {
-        // direct Jacobi for n <= 128, tridiagonalisation + divide and conquer above; only enqueues work
+        // direct Jacobi for n <= 64, tridiagonalisation + divide and conquer above; only enqueues work
         KFACB_REQUIRE(workspace && !((uintptr_t)workspace & 255), "eigh workspace missing or misaligned");
         for (int i = 0; i < count; ++i)
             if (n[i] > 0) KFACB_REQUIRE(M[i] && Q[i] && d[i], "matrix %d: null pointer", i);
@@ -1136,7 +1140,7 @@ extern "C" int kfacb_eigh_batched(const int32_t* n, int32_t count,
         struct IdxGuard { int* p; ~IdxGuard() { delete[] p; } } idx_guard{idx};
         const int nb = collect_blocked(n, count, idx);
         int n_direct = 0;
-        for (int i = 0; i < count; ++i) n_direct += (n[i] > 0 && n[i] <= DIRECT_MAX_N);
+        for (int i = 0; i < count; ++i) n_direct += (n[i] > 0 && n[i] <= TDC_DIRECT_N);
         const size_t dbytes = direct_tables_bytes(count - nb);
         if (workspace_bytes < dbytes) { set_error("eigh workspace too small"); return KFACB_ERR_WORKSPACE; }
         char* ws = (char*)workspace;
@@ -1145,7 +1149,7 @@ extern "C" int kfacb_eigh_batched(const int32_t* n, int32_t count,
             int* hidx = new int[n_direct];
             int k = 0, nmax = 0;
             for (int i = 0; i < count; ++i) {
-                if (n[i] <= 0 || n[i] > DIRECT_MAX_N) continue;
+                if (n[i] <= 0 || n[i] > TDC_DIRECT_N) continue;
                 hm[k] = DirectMat{M[i], Q[i], d[i], n[i]};
                 hidx[k] = i;
                 if (n[i] > nmax) nmax = n[i];

@@ -436,6 +436,54 @@ __device__ __forceinline__ void tile_product(bool tc, const LA& la, const LB& lb
             for (int j = 0; j < 8; ++j) epi(frag_row(i), frag_col(j), acc[i][j]);
     }
 }
+// Same, for a read-modify-write epilogue  *addr(m, n) -= value  (addr returns nullptr outside the matrix): the old
+// values of a batch are loaded BEFORE its stores -- written as `Z[i] -= v` per element the compiler must assume that a
+// store aliases the next load and serialises one L2 round trip per element (measured: 40 us per 128x128 tile).
+template <class LA, class LB, class Addr>
+__device__ __forceinline__ void tile_product_sub(bool tc, const LA& la, const LB& lb, int m0, int n0, int kbeg, int kend,
+                                                 const Addr& addr) {
+    extern __shared__ __align__(128) unsigned char dsm_raw[];
+    if (tc) {
+        __shared__ __align__(8) uint64_t mbar;
+        __shared__ uint32_t tmem_slot;
+        tcg::Ctx c;
+        tcg::setup_hp(c, dsm_raw, &mbar, &tmem_slot);
+        tcg::mainloop_hp(la, lb, m0, n0, kbeg, kend, false, c);
+        const float* d = tcg::drain_hp(c, kend > kbeg);
+        constexpr int BATCH = 16;
+        for (int e0 = threadIdx.x; e0 < TILE * TILE; e0 += tcg::THREADS * BATCH) {
+            float* p[BATCH]; float old[BATCH];
+#pragma unroll
+            for (int b = 0; b < BATCH; ++b) {
+                const int e = e0 + b * tcg::THREADS;
+                p[b] = addr(e >> 7, e & 127);
+                old[b] = p[b] ? *p[b] : 0.f;
+            }
+#pragma unroll
+            for (int b = 0; b < BATCH; ++b) {
+                const int e = e0 + b * tcg::THREADS;
+                if (p[b]) *p[b] = old[b] - d[(e >> 7) * tcg::DPITCH + (e & 127)];
+            }
+        }
+        tcg::teardown_hp(c);
+    } else {
+        GemmSmem& sm = *reinterpret_cast<GemmSmem*>(dsm_raw);
+        float acc[8][8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+        gemm_mainloop(la, lb, m0, n0, kbeg, kend, sm, acc);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            float* p[8]; float old[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { p[j] = addr(frag_row(i), frag_col(j)); old[j] = p[j] ? *p[j] : 0.f; }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) if (p[j]) *p[j] = old[j] - acc[i][j];
+        }
+    }
+}
 static_assert(sizeof(GemmSmem) <= tcg::SMEM, "the SIMT core runs in the tensor-core core's dynamic shared memory");
 // Matrices up to this size run their GEMM-shaped stages on the exact-fp32 SIMT core: their flops are negligible
 // (sum n^3 over them is < 3 % of a ResNet-50 step) and the small, tightly clustered factors (conv1: n = 147 with
@@ -675,18 +723,24 @@ bt_upd_kernel(const DcMat* mats, const Tile* tiles, int force) {
     const int m0 = tl.b * TILE, n0 = tl.c * TILE, n = mt.n;
     float* Z = mt.Z[mt.fin];
     const long ldz = mt.ldz;
-    tile_product(use_tc_for(mt.n, force), la, lb, m0, n0, 0, PB, false, [=](int m, int c, float v) {
+    tile_product_sub(use_tc_for(mt.n, force), la, lb, m0, n0, 0, PB, [=](int m, int c) -> float* {
         const int cc = jb + n0 + c;
-        if (m0 + m < n && cc < n) Z[(size_t)(m0 + m) * ldz + cc] -= v;
+        return (m0 + m < n && cc < n) ? Z + (size_t)(m0 + m) * ldz + cc : nullptr;
     });
 }
 
-// Q[r][c] = Zt[c][r], d = lam * (lam > eps)
-__global__ void eig_write_kernel(const DcMat* mats, float eps_floor, int32_t* sweeps_out, const int* out_index) {
+// Q[r][c] = Zt[c][r], d = lam * (lam > eps).  One CTA per 32x32 tile; tile_prefix[a] = tiles of the matrices before a
+// (the CTA finds its matrix by bisection: no per-tile table, no empty CTAs).
+__global__ void eig_write_kernel(const DcMat* mats, const int* tile_prefix, int nb, float eps_floor, int32_t* sweeps_out,
+                                 const int* out_index) {
     __shared__ float t[32][33];
-    const DcMat mt = mats[blockIdx.z];
-    const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
-    if (c0 >= mt.n || r0 >= mt.n) return;
+    int lo = 0, hi = nb - 1;
+    while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (tile_prefix[mid] <= (int)blockIdx.x) lo = mid; else hi = mid - 1; }
+    const DcMat mt = mats[lo];
+    const int local = blockIdx.x - tile_prefix[lo];
+    const int nt = (mt.n + 31) >> 5;
+    const int by = local / nt, bx = local - by * nt;
+    const int c0 = bx * 32, r0 = by * 32;
     const float* Zt = mt.Z[mt.fin];
     const int lx = threadIdx.x & 31, ly = threadIdx.x >> 5;
     for (int cc = ly; cc < 32; cc += 8) {
@@ -698,10 +752,10 @@ __global__ void eig_write_kernel(const DcMat* mats, float eps_floor, int32_t* sw
         const int r = r0 + rr, c = c0 + lx;
         if (r < mt.n && c < mt.n) mt.Q[(size_t)r * mt.n + c] = t[lx][rr];
     }
-    if (blockIdx.y == 0 && ly == 0) {
+    if (by == 0 && ly == 0) {
         const int c = c0 + lx;
         if (c < mt.n) { const float v = mt.dcur[mt.fin][c]; mt.dout[c] = v > eps_floor ? v : 0.f; }
-        if (blockIdx.x == 0 && lx == 0 && sweeps_out) sweeps_out[out_index[blockIdx.z]] = 1;
+        if (bx == 0 && lx == 0 && sweeps_out) sweeps_out[out_index[lo]] = 1;
     }
 }
 
@@ -710,7 +764,7 @@ __global__ void eig_write_kernel(const DcMat* mats, float eps_floor, int32_t* sw
 // ---------------------------------------------------------------------------
 struct MatLayout {
     int n, ldz, npanels, nks, nleaf, depth;
-    size_t T, Z0, Z1, U, Ypart, Y2, Tb, vecs, Vp, Wp, part, ints, rotcs;
+    size_t T, Z0, Z1, U, Ypart, Y2, Tb, vecs, Vp, Wp, part, zpart, ints, rotcs;
 };
 struct Plan {
     int nb = 0, sms = 148, grid = 0, nlevels = 0, nmax = 0, max_panels = 0;
@@ -726,12 +780,12 @@ struct Plan {
     std::vector<Tile> y_tiles, yt_tiles, upd_tiles; std::vector<int> y_off, yt_off, upd_off;   // per iteration
     // offsets inside the workspace
     size_t off_tables = 0, off_zero = 0, zero_bytes = 0, off_mats = 0, total = 0;
-    size_t t_jobs = 0, t_mats = 0, t_src = 0, t_oidx = 0, t_cta = 0, t_ent = 0, t_leaves = 0, t_merges = 0, t_gemm = 0,
+    size_t t_jobs = 0, t_mats = 0, t_src = 0, t_oidx = 0, t_wpre = 0, t_cta = 0, t_ent = 0, t_leaves = 0, t_merges = 0, t_gemm = 0,
            t_panels = 0, t_y = 0, t_yt = 0, t_upd = 0, tables_bytes = 0;
     size_t z_bar = 0, z_states = 0, z_prof = 0;
 };
 
-static int round4(int n) { return (n + 3) & ~3; }
+static int round8(int n) { return (n + 7) & ~7; }     // row pitch: 8-row blocks of the tridiagonalisation read 32-byte slices
 
 static void leaf_bounds(int n, std::vector<int>& b) {
     const int L = (n + LEAF - 1) / LEAF;
@@ -757,7 +811,7 @@ static void build_plan(const int32_t* n, const int* idx, int nb, Plan& pl) {
     std::vector<std::vector<int>> bounds(nb);
     for (int a = 0; a < nb; ++a) {
         MatLayout& m = pl.ml[a];
-        m.n = ns[a]; m.ldz = round4(m.n);
+        m.n = ns[a]; m.ldz = round8(m.n);
         m.npanels = (m.n - 1 + PB - 1) / PB;
         m.nks = (m.ldz + YCH - 1) / YCH;
         leaf_bounds(m.n, bounds[a]);
@@ -825,6 +879,7 @@ static void build_plan(const int32_t* n, const int* idx, int nb, Plan& pl) {
     pl.t_mats = ttake(sizeof(DcMat) * (nb + 1));
     pl.t_src = ttake(sizeof(void*) * (nb + 1));
     pl.t_oidx = ttake(sizeof(int) * (nb + 1));
+    pl.t_wpre = ttake(sizeof(int) * (nb + 2));
     pl.t_cta = ttake(sizeof(int) * pl.cta_begin.size());
     pl.t_ent = ttake(sizeof(int) * pl.entries.size());
     pl.t_leaves = ttake(sizeof(DcLeaf) * (pl.leaves.size() + 1));
@@ -856,6 +911,7 @@ static void build_plan(const int32_t* n, const int* idx, int nb, Plan& pl) {
         m.Vp = take((size_t)m.n * trd::NB * sizeof(float));
         m.Wp = take((size_t)m.n * trd::NB * sizeof(float));
         m.part = take((size_t)trd::NPART * trd::TS * sizeof(float));
+        m.zpart = take((size_t)pl.team[a] * m.ldz * sizeof(float));
         m.ints = take((size_t)4 * m.ldz * sizeof(int));
         m.rotcs = take((size_t)2 * m.ldz * sizeof(float));
     }
@@ -903,7 +959,7 @@ int eigh_tdc_last_profile(double* out8) {
 extern "C" int kfacb_eigh_plan_teams(const int32_t* n, int32_t count, int32_t sms, int32_t* team_out) {
     if (!n || !team_out || count < 0 || sms <= 0) return -1;
     std::vector<int> ns, idx, team, cta(sms + 1, 0);
-    for (int i = 0; i < count; ++i) { team_out[i] = 0; if (n[i] > kfacb::DIRECT_MAX_N) { ns.push_back(n[i]); idx.push_back(i); } }
+    for (int i = 0; i < count; ++i) { team_out[i] = 0; if (n[i] > 64) { ns.push_back(n[i]); idx.push_back(i); } }
     if (ns.empty()) return 0;
     team.assign(ns.size(), 1);
     std::vector<int> entries((size_t)2 * ns.size() * sms + 2, 0);
@@ -938,6 +994,8 @@ int eigh_tdc_run(const int32_t* n, const int* idx, int nb, const float* const* M
     DcMat* mats = reinterpret_cast<DcMat*>(img.data() + pl.t_mats);
     const float** srcp = reinterpret_cast<const float**>(img.data() + pl.t_src);
     int* oidx = reinterpret_cast<int*>(img.data() + pl.t_oidx);
+    int* wpre = reinterpret_cast<int*>(img.data() + pl.t_wpre);
+    int write_tiles = 0;
     char* zero = ws + pl.off_zero;
     for (int a = 0; a < nb; ++a) {
         const MatLayout& m = pl.ml[a];
@@ -949,6 +1007,7 @@ int eigh_tdc_run(const int32_t* n, const int* idx, int nb, const float* const* M
         jb.d = V(0); jb.e = V(1); jb.tau = V(2); jb.x = V(3); jb.y = V(4);
         jb.Vp = reinterpret_cast<float*>(ws + m.Vp); jb.Wp = reinterpret_cast<float*>(ws + m.Wp);
         jb.part = reinterpret_cast<float*>(ws + m.part);
+        jb.zpart = reinterpret_cast<float*>(ws + m.zpart);
         jb.bar = reinterpret_cast<unsigned*>(zero + pl.z_bar + (size_t)128 * a);
         jb.n = m.n; jb.ldt = m.ldz; jb.team = pl.team[a];
         jb.prof = trd_prof ? reinterpret_cast<long long*>(zero + pl.z_prof) + 16 * a : nullptr;
@@ -964,6 +1023,8 @@ int eigh_tdc_run(const int32_t* n, const int* idx, int nb, const float* const* M
         mt.n = m.n; mt.ldz = m.ldz; mt.npanels = m.npanels; mt.fin = m.depth & 1;
         srcp[a] = M[idx[a]];
         oidx[a] = idx[a];
+        wpre[a] = write_tiles;
+        write_tiles += ((m.n + 31) / 32) * ((m.n + 31) / 32);
     }
     memcpy(img.data() + pl.t_cta, pl.cta_begin.data(), sizeof(int) * pl.cta_begin.size());
     memcpy(img.data() + pl.t_ent, pl.entries.data(), sizeof(int) * pl.entries.size());
@@ -1079,8 +1140,8 @@ int eigh_tdc_run(const int32_t* n, const int* idx, int nb, const float* const* M
         }
     }
     // ---- (4) floor + write ----
-    eig_write_kernel<<<dim3(cdiv(pl.nmax, 32), cdiv(pl.nmax, 32), nb), 256, 0, st>>>(
-        d_mats, eps_floor, sweeps_out, reinterpret_cast<const int*>(tb + pl.t_oidx));
+    eig_write_kernel<<<write_tiles, 256, 0, st>>>(d_mats, reinterpret_cast<const int*>(tb + pl.t_wpre), nb, eps_floor, sweeps_out,
+                                                  reinterpret_cast<const int*>(tb + pl.t_oidx));
     KFACB_CHECK_LAUNCH();
     if (sev) cudaEventRecord(sev->ev[3], st);
     return KFACB_OK;

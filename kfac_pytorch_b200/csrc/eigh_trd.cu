@@ -32,6 +32,8 @@ constexpr int OP_PITCH = 132;                                   // 128 + 4: floa
 
 struct __align__(16) Smem {
     float v[MAXN];                                              // reflector of the current column (absolute index)
+    float z[MAXN];                                              // this CTA's transposed contributions  z_c = sum_{own rows i > c} T[i][c] v_i
+    float ysum[MAXN];                                           // row sums of the CTA's own blocks: [8 k + u] = row u of its k-th owned block
     float op[4][NB][OP_PITCH];                                  // rank-2k update operands: V_I, W_I, W_J, V_J (k-major)
     float red[3][NWARP][33];
     float q[72];                                                // team-reduced partial sums: [0,32) W^T v, [32,64) V^T v, [64] v.y, [65] |x|^2
@@ -56,10 +58,15 @@ __device__ __forceinline__ void team_barrier(unsigned* ctr, unsigned& target, in
     }
 }
 
-__device__ __forceinline__ int first_own(int r0, int rank, int team) {
-    int o = rank - r0 % team;
+// Rows are dealt to the team in BLOCKS of 8 consecutive rows (block b -> CTA b mod team): the 8 rows of a block have
+// the same length in the lower triangle (one warp streams them together, 8 loads in flight per lane) and their
+// slice of any per-row vector is one 32-byte sector.  First block owned by `rank` that contains a row >= r0:
+constexpr int RBLK = 8;
+__device__ __forceinline__ int first_block(int r0, int rank, int team) {
+    const int b0 = r0 >> 3;
+    int o = rank - b0 % team;
     if (o < 0) o += team;
-    return r0 + o;
+    return b0 + o;
 }
 
 // Team-wide sums of the partial sums of the last product pass + what finishing column `kc` of W needs.
@@ -75,7 +82,14 @@ __device__ __forceinline__ void reduce_and_prologue(const Job& jb, Smem& sm, int
     if (warp == 0 && want_row) {
         vj = lane <= kc ? __ldcg(jb.Vp + (size_t)row_j * NB + lane) : 0.f;
         wj = lane < kc ? __ldcg(jb.Wp + (size_t)row_j * NB + lane) : 0.f;
-        yj = __ldcg(jb.y + row_j);
+        // y_j = own lower-triangle part + every CTA's transposed contributions to row j
+        float zz = 0.f;
+#pragma unroll
+        for (int it = 0; it < TS / 32; ++it) {
+            const int r = lane + 32 * it;
+            if (r < jb.team) zz += __ldcg(jb.zpart + (size_t)r * jb.ldt + row_j);
+        }
+        yj = __ldcg(jb.y + row_j) + warp_sum(zz);
     }
     constexpr int PER = (65 + NWARP - 1) / NWARP;               // quantities per warp
     float a[PER];
@@ -175,22 +189,62 @@ __device__ void rank2k_update(const Job& jb, Smem& sm, int R0, int kc, int rank)
                 for (int b = 0; b < 4; ++b) acc[a][b] = fmaf(va[a], wb[b], fmaf(wa[a], vb[b], acc[a][b]));
         }
         const int gc = R0 + 128 * tj + col4;
+        if (aligned && gc + 3 < n) {
+            // all eight old rows in flight before the first store (a store may alias the next load for the compiler)
+            float4 c[8];
 #pragma unroll
-        for (int a = 0; a < 8; ++a) {
-            const int gi = R0 + 128 * ti + row8 + a;
-            if (gi >= n) continue;
-            float* p = jb.T + (size_t)gi * ldt + gc;
-            if (aligned && gc + 3 < n) {
-                float4 c = __ldcg(reinterpret_cast<const float4*>(p));
-                c.x -= acc[a][0]; c.y -= acc[a][1]; c.z -= acc[a][2]; c.w -= acc[a][3];
-                *reinterpret_cast<float4*>(p) = c;
-            } else {
+            for (int a = 0; a < 8; ++a) {
+                const int gi = R0 + 128 * ti + row8 + a;
+                c[a] = gi < n ? __ldcg(reinterpret_cast<const float4*>(jb.T + (size_t)gi * ldt + gc)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int a = 0; a < 8; ++a) {
+                const int gi = R0 + 128 * ti + row8 + a;
+                if (gi < n) {
+                    c[a].x -= acc[a][0]; c[a].y -= acc[a][1]; c[a].z -= acc[a][2]; c[a].w -= acc[a][3];
+                    *reinterpret_cast<float4*>(jb.T + (size_t)gi * ldt + gc) = c[a];
+                }
+            }
+        } else {
+#pragma unroll
+            for (int a = 0; a < 8; ++a) {
+                const int gi = R0 + 128 * ti + row8 + a;
+                if (gi >= n) continue;
+                float* p = jb.T + (size_t)gi * ldt + gc;
 #pragma unroll
                 for (int b = 0; b < 4; ++b)
                     if (gc + b < n) p[b] = __ldcg(p + b) - acc[a][b];
             }
         }
     }
+}
+
+// y_i of the 8 rows of block `blk` (rows 8 blk .. 8 blk + 7): the own lower-triangle part jb.y plus the team's
+// transposed contributions zpart[r][i].  Lane l sums CTAs r = l, l + 32, ..; the 8 reductions are interleaved.
+__device__ __forceinline__ void assemble_y(const Job& jb, int blk, float (&y8)[RBLK]) {
+    const int lane = threadIdx.x & 31;
+    float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0;
+    const int i0 = blk * RBLK;
+#pragma unroll
+    for (int it = 0; it < TS / 32; ++it) {
+        const int r = lane + 32 * it;
+        if (r < jb.team) {
+            const float4* z = reinterpret_cast<const float4*>(jb.zpart + (size_t)r * jb.ldt + i0);
+            const float4 z0 = __ldcg(z), z1 = __ldcg(z + 1);
+            a0.x += z0.x; a0.y += z0.y; a0.z += z0.z; a0.w += z0.w;
+            a1.x += z1.x; a1.y += z1.y; a1.z += z1.z; a1.w += z1.w;
+        }
+    }
+    float s[RBLK] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+        for (int u = 0; u < RBLK; ++u) s[u] += __shfl_xor_sync(0xffffffffu, s[u], o);
+    const float4* yl = reinterpret_cast<const float4*>(jb.y + i0);
+    const float4 y0 = __ldcg(yl), y1 = __ldcg(yl + 1);
+    const float yo[RBLK] = {y0.x, y0.y, y0.z, y0.w, y1.x, y1.y, y1.z, y1.w};
+#pragma unroll
+    for (int u = 0; u < RBLK; ++u) y8[u] = yo[u] + s[u];
 }
 
 __device__ void run_job(const Job& jb, int rank, Smem& sm) {
@@ -208,54 +262,51 @@ __device__ void run_job(const Job& jb, int rank, Smem& sm) {
     for (int j = 0; j < n - 1; ++j) {
         const int jp = j - j0;
         // ---------------- phase A: finish w_{j-1} (rows >= j), form column j and |x|^2 ----------------
-        if (jp > 0) {
-            reduce_and_prologue(jb, sm, jp - 1, j, true);
-        }
+        if (jp > 0) reduce_and_prologue(jb, sm, jp - 1, j, true);
         TRD_TICK(0);
         {
             const float tau_p = sm.tau, cw = sm.cw;
             float nrm = 0.f;
-            // AR rows per warp iteration: their loads are all issued before the first dependent reduction
-            constexpr int AR = 4;
-            for (int i0 = first_own(j, rank, team) + team * warp; i0 < n; i0 += team * NWARP * AR) {
-                float vk[AR], wk[AR], yi[AR], tji[AR];
+            // one 8-row block per warp iteration: all loads of the block are issued before the first reduction
+            for (int blk = first_block(j, rank, team) + team * warp; blk * RBLK < n; blk += team * NWARP) {
+                float vk[RBLK], wk[RBLK], yi[RBLK], tji[RBLK];
 #pragma unroll
-                for (int u = 0; u < AR; ++u) {
-                    const int i = i0 + u * team * NWARP;
-                    const bool ok = i < n;
+                for (int u = 0; u < RBLK; ++u) {
+                    const int i = blk * RBLK + u;
+                    const bool ok = i >= j && i < n;
                     vk[u] = (ok && lane < jp) ? __ldcg(jb.Vp + (size_t)i * NB + lane) : 0.f;
                     wk[u] = (ok && lane < jp - 1) ? __ldcg(jb.Wp + (size_t)i * NB + lane) : 0.f;
-                    yi[u] = (ok && jp > 0) ? __ldcg(jb.y + i) : 0.f;
                     tji[u] = ok ? __ldcg(jb.T + (size_t)j * ldt + i) : 0.f;
                 }
-                if (jp > 0) {                                       // the AR reductions are independent: interleaved by the unrolling
-                    float dot[AR];
+                if (jp > 0) {
+                    assemble_y(jb, blk, yi);
+                    float dot[RBLK];
 #pragma unroll
-                    for (int u = 0; u < AR; ++u) dot[u] = lane < jp - 1 ? vk[u] * sm.q[lane] + wk[u] * sm.q[32 + lane] : 0.f;
+                    for (int u = 0; u < RBLK; ++u) dot[u] = lane < jp - 1 ? vk[u] * sm.q[lane] + wk[u] * sm.q[32 + lane] : 0.f;
 #pragma unroll
                     for (int o = 16; o > 0; o >>= 1)
 #pragma unroll
-                        for (int u = 0; u < AR; ++u) dot[u] += __shfl_xor_sync(0xffffffffu, dot[u], o);
+                        for (int u = 0; u < RBLK; ++u) dot[u] += __shfl_xor_sync(0xffffffffu, dot[u], o);
 #pragma unroll
-                    for (int u = 0; u < AR; ++u) {
-                        const int i = i0 + u * team * NWARP;
+                    for (int u = 0; u < RBLK; ++u) {
+                        const int i = blk * RBLK + u;
                         const float vlast = __shfl_sync(0xffffffffu, vk[u], jp - 1);
                         const float wnew = tau_p * (yi[u] - dot[u]) - cw * vlast;
-                        if (lane == jp - 1 && i < n) { wk[u] = wnew; jb.Wp[(size_t)i * NB + lane] = wnew; }
+                        if (lane == jp - 1 && i >= j && i < n) { wk[u] = wnew; jb.Wp[(size_t)i * NB + lane] = wnew; }
                     }
                 }
-                float corr[AR];
+                float corr[RBLK];
 #pragma unroll
-                for (int u = 0; u < AR; ++u) corr[u] = lane < jp ? vk[u] * sm.rowW[lane] + wk[u] * sm.rowV[lane] : 0.f;
+                for (int u = 0; u < RBLK; ++u) corr[u] = lane < jp ? vk[u] * sm.rowW[lane] + wk[u] * sm.rowV[lane] : 0.f;
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1)
 #pragma unroll
-                    for (int u = 0; u < AR; ++u) corr[u] += __shfl_xor_sync(0xffffffffu, corr[u], o);
+                    for (int u = 0; u < RBLK; ++u) corr[u] += __shfl_xor_sync(0xffffffffu, corr[u], o);
 #pragma unroll
-                for (int u = 0; u < AR; ++u) {
-                    const int i = i0 + u * team * NWARP;
+                for (int u = 0; u < RBLK; ++u) {
+                    const int i = blk * RBLK + u;
                     const float xi = tji[u] - corr[u];
-                    if (lane == 0 && i < n) {
+                    if (lane == 0 && i >= j && i < n) {
                         if (i == j) jb.d[j] = xi;
                         else { jb.x[i] = xi; if (i >= j + 2) nrm = fmaf(xi, xi, nrm); }
                     }
@@ -272,7 +323,7 @@ __device__ void run_job(const Job& jb, int rank, Smem& sm) {
         TRD_TICK(1);
         team_barrier(jb.bar, target, team);
         TRD_TICK(2);
-        // ---------------- phase B: reflector, y = T v, panel inner products ----------------
+        // ---------------- phase B: reflector, y = T v (lower triangle only), panel inner products ----------------
         const int c_al = (j + 1) & ~3;
         constexpr int XR = MAXN / THREADS;
         float xr[XR];                                            // raw column, in flight while |x|^2 is being reduced
@@ -308,73 +359,124 @@ __device__ void run_job(const Job& jb, int rank, Smem& sm) {
 #pragma unroll
             for (int u = 0; u < XR; ++u) {
                 const int c = c_al + tid + u * THREADS;
-                if (c < ldt) sm.v[c] = (c == j + 1) ? 1.f : xr[u] * scale;
+                if (c < ldt) { sm.v[c] = (c == j + 1) ? 1.f : xr[u] * scale; sm.z[c] = 0.f; }
             }
         }
         __syncthreads();
         TRD_TICK(3);
         {
-            float acc_s = 0.f, acc_t = 0.f, acc_vy = 0.f;
-            const int q_beg = c_al >> 2, q_end = ldt >> 2;
-            // RB rows x LD predicated 16-byte loads per lane in flight (RB * LD = 8), chosen by the row length:
-            // long rows stream one row at a time, short rows (small matrices, the tail of every matrix) go RB at once
-            const int qlen = q_end - q_beg;
-            auto rows_product = [&](auto rb_tag, auto ld_tag) {
-                constexpr int RB = decltype(rb_tag)::value, LD = decltype(ld_tag)::value;
-                for (int i0 = first_own(j + 1, rank, team) + team * warp; i0 < n; i0 += team * NWARP * RB) {
-                    float wpi[RB], vpi[RB], acc[RB];
+            // Symmetric product from the LOWER triangle (half the bytes).  Element T[i][c], c <= i, feeds the row sum
+            // y_i += T[i][c] v_c and, for c < i, the transposed half z_c += T[i][c] v_i.  Work unit = (owned 8-row
+            // block k, chunk of 32 quads = 128 columns): a warp loads the 8 rows of the chunk together (8 x 16 bytes
+            // in flight per lane), sums the transposed half over the 8 rows in registers (one shared-memory atomic
+            // per column) and reduces the 8 row partials over its lanes into shared-memory row accumulators.
+            // Blocks have very different lengths in the lower triangle, so the units are dealt chunk-major and
+            // zig-zag (chunk c -> warp c mod 16, reversed every other round): every warp gets long and short blocks.
+            const int q_beg = c_al >> 2;
+            const int b_first = first_block(j + 1, rank, team);
+            const int K = b_first * RBLK < n ? ((n - 1) / RBLK - b_first) / team + 1 : 0;      // owned blocks this column
+            for (int e = tid; e < K * RBLK; e += THREADS) sm.ysum[e] = 0.f;
+            __syncthreads();
+            const int q_hi = K > 0 ? 2 * (b_first + (K - 1) * team) + 1 : -1;                   // last quad of the longest block
+            const int nchunk = q_hi >= q_beg ? (q_hi - q_beg) / 32 + 1 : 0;
+            for (int c0 = 0; c0 < nchunk; c0 += 2 * NWARP) {
+                for (int half = 0; half < 2; ++half) {
+                    const int c = c0 + (half == 0 ? warp : 2 * NWARP - 1 - warp);
+                    if (c >= nchunk) continue;
+                    const int q = q_beg + 32 * c + lane;
+                    // first block that reaches this chunk: 2 blk + 1 >= q_beg + 32 c
+                    int kmin = ((q_beg + 32 * c) / 2 - b_first + team - 1) / team;
+                    if (kmin < 0) kmin = 0;
+                    const float4 vv = *reinterpret_cast<const float4*>(&sm.v[4 * (q < (ldt >> 2) ? q : q_beg)]);
+                    float4 zc = make_float4(0.f, 0.f, 0.f, 0.f);
+                    for (int k = kmin; k < K; ++k) {
+                        const int i0 = (b_first + k * team) * RBLK;
+                        float4 m[RBLK];
 #pragma unroll
-                    for (int u = 0; u < RB; ++u) {
-                        const int i = i0 + u * team * NWARP;
-                        wpi[u] = (i < n && lane < jp) ? __ldcg(jb.Wp + (size_t)i * NB + lane) : 0.f;
-                        vpi[u] = (i < n && lane < jp) ? __ldcg(jb.Vp + (size_t)i * NB + lane) : 0.f;
-                        acc[u] = 0.f;
+                        for (int u = 0; u < RBLK; ++u) {
+                            const int i = i0 + u;
+                            m[u] = (i > j && i < n && 4 * q <= i)
+                                       ? __ldcg(reinterpret_cast<const float4*>(jb.T + (size_t)i * ldt) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+                        }
+                        float acc[RBLK];
+                        const bool edge = 4 * q + 3 >= i0;            // this quad touches the diagonal of some row of the block
+#pragma unroll
+                        for (int u = 0; u < RBLK; ++u) {
+                            float4 t = m[u];
+                            const int i = i0 + u;
+                            const float vi = (i > j && i < n) ? sm.v[i] : 0.f;
+                            if (edge) {                               // c <= i for the row sum, c < i for the transposed half
+                                const int cc = 4 * q;
+                                if (cc > i) t.x = 0.f;
+                                if (cc + 1 > i) t.y = 0.f;
+                                if (cc + 2 > i) t.z = 0.f;
+                                if (cc + 3 > i) t.w = 0.f;
+                                acc[u] = fmaf(t.x, vv.x, fmaf(t.y, vv.y, fmaf(t.z, vv.z, t.w * vv.w)));
+                                if (cc == i) t.x = 0.f;
+                                if (cc + 1 == i) t.y = 0.f;
+                                if (cc + 2 == i) t.z = 0.f;
+                                if (cc + 3 == i) t.w = 0.f;
+                            } else {
+                                acc[u] = fmaf(t.x, vv.x, fmaf(t.y, vv.y, fmaf(t.z, vv.z, t.w * vv.w)));
+                            }
+                            zc.x = fmaf(t.x, vi, zc.x); zc.y = fmaf(t.y, vi, zc.y);
+                            zc.z = fmaf(t.z, vi, zc.z); zc.w = fmaf(t.w, vi, zc.w);
+                        }
+#pragma unroll
+                        for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+                            for (int u = 0; u < RBLK; ++u) acc[u] += __shfl_xor_sync(0xffffffffu, acc[u], o);
+                        float mine = acc[0];
+#pragma unroll
+                        for (int u = 1; u < RBLK; ++u) if (lane == u) mine = acc[u];
+                        if (lane < RBLK) atomicAdd(&sm.ysum[k * RBLK + lane], mine);
                     }
-                    for (int q = q_beg + lane; q < q_end; q += 32 * LD) {
-                        float4 m[RB][LD];
-#pragma unroll
-                        for (int u = 0; u < RB; ++u) {
-                            const int i = i0 + u * team * NWARP;
-                            const float4* row = reinterpret_cast<const float4*>(jb.T + (size_t)(i < n ? i : i0) * ldt);
-#pragma unroll
-                            for (int l = 0; l < LD; ++l)
-                                m[u][l] = (i < n && q + 32 * l < q_end) ? __ldcg(row + q + 32 * l) : make_float4(0.f, 0.f, 0.f, 0.f);
-                        }
-#pragma unroll
-                        for (int l = 0; l < LD; ++l) {
-                            const int qq = (q + 32 * l < q_end) ? q + 32 * l : q;
-                            const float4 vv = *reinterpret_cast<const float4*>(&sm.v[4 * qq]);
-#pragma unroll
-                            for (int u = 0; u < RB; ++u)
-                                acc[u] += fmaf(m[u][l].x, vv.x, fmaf(m[u][l].y, vv.y, fmaf(m[u][l].z, vv.z, m[u][l].w * vv.w)));
-                        }
-                    }
-#pragma unroll
-                    for (int u = 0; u < RB; ++u) {
-                        const int i = i0 + u * team * NWARP;
-                        if (i >= n) break;
-                        const float yi = warp_sum(acc[u]);
-                        const float vi = sm.v[i];
-                        acc_s = fmaf(wpi[u], vi, acc_s);
-                        acc_t = fmaf(vpi[u], vi, acc_t);
-                        if (lane == 0) {
-                            jb.y[i] = yi;
-                            acc_vy = fmaf(vi, yi, acc_vy);
-                            jb.Vp[(size_t)i * NB + jp] = vi;
-                            jb.T[(size_t)j * ldt + i] = vi;
-                        }
+                    if (q < (ldt >> 2)) {
+                        atomicAdd(&sm.z[4 * q], zc.x); atomicAdd(&sm.z[4 * q + 1], zc.y);
+                        atomicAdd(&sm.z[4 * q + 2], zc.z); atomicAdd(&sm.z[4 * q + 3], zc.w);
                     }
                 }
-            };
-            using I1 = std::integral_constant<int, 1>; using I2 = std::integral_constant<int, 2>;
-            using I4 = std::integral_constant<int, 4>; using I8 = std::integral_constant<int, 8>;
-            if (qlen > 128) rows_product(I1{}, I8{});
-            else if (qlen > 32) rows_product(I2{}, I4{});
-            else rows_product(I8{}, I1{});
+            }
             TRD_TICK(4);
+            __syncthreads();                                       // row sums and z complete
+            // per owned row: publish the own part of y, the reflector, and the panel inner products
+            float acc_s = 0.f, acc_t = 0.f, acc_vy = 0.f;
+            for (int k = warp; k < K; k += NWARP) {
+                const int i0 = (b_first + k * team) * RBLK;
+                float wpi[RBLK], vpi[RBLK];
+#pragma unroll
+                for (int u = 0; u < RBLK; ++u) {                      // all panel rows of the block in flight before the stores
+                    const int i = i0 + u;
+                    const bool ok = i > j && i < n && lane < jp;
+                    wpi[u] = ok ? __ldcg(jb.Wp + (size_t)i * NB + lane) : 0.f;
+                    vpi[u] = ok ? __ldcg(jb.Vp + (size_t)i * NB + lane) : 0.f;
+                }
+#pragma unroll
+                for (int u = 0; u < RBLK; ++u) {
+                    const int i = i0 + u;
+                    if (i <= j || i >= n) continue;
+                    const float vi = sm.v[i], yl = sm.ysum[k * RBLK + u];
+                    acc_s = fmaf(wpi[u], vi, acc_s);
+                    acc_t = fmaf(vpi[u], vi, acc_t);
+                    if (lane == 0) {
+                        jb.y[i] = yl;                                  // own (lower-triangle) part of y_i
+                        acc_vy = fmaf(vi, yl, acc_vy);
+                        jb.Vp[(size_t)i * NB + jp] = vi;
+                        jb.T[(size_t)j * ldt + i] = vi;
+                    }
+                }
+            }
+            // hand z to the team (coalesced) and fold its share of v.y:  v.y = sum_i v_i ylow_i + sum_c v_c z_c
+            float vz = 0.f;
+            for (int c = c_al + tid; c < ldt; c += THREADS) {
+                const float zc = sm.z[c];
+                jb.zpart[(size_t)rank * ldt + c] = zc;
+                vz = fmaf(sm.v[c], zc, vz);
+            }
+            vz = warp_sum(vz);
             sm.red[0][warp][lane] = acc_s;
             sm.red[1][warp][lane] = acc_t;
-            if (lane == 0) sm.red[2][warp][0] = acc_vy;
+            if (lane == 0) sm.red[2][warp][0] = acc_vy + vz;
             __syncthreads();
             if (warp == 0) {
                 float s = 0.f, t = 0.f, vy = 0.f;
@@ -391,13 +493,28 @@ __device__ void run_job(const Job& jb, int rank, Smem& sm) {
         if (jp == NB - 1 || j == n - 2) {
             reduce_and_prologue(jb, sm, jp, 0, false);
             const float tau_p = sm.tau, cw = sm.cw;
-            for (int i = first_own(j + 1, rank, team) + team * warp; i < n; i += team * NWARP) {
-                const float vk = lane <= jp ? __ldcg(jb.Vp + (size_t)i * NB + lane) : 0.f;
-                const float wk = lane < jp ? __ldcg(jb.Wp + (size_t)i * NB + lane) : 0.f;
-                const float dot = warp_sum(lane < jp ? vk * sm.q[lane] + wk * sm.q[32 + lane] : 0.f);
-                const float yi = __ldcg(jb.y + i);
-                const float vlast = __shfl_sync(0xffffffffu, vk, jp);
-                if (lane == jp) jb.Wp[(size_t)i * NB + lane] = tau_p * (yi - dot) - cw * vlast;
+            for (int blk = first_block(j + 1, rank, team) + team * warp; blk * RBLK < n; blk += team * NWARP) {
+                float vk[RBLK], wk[RBLK], yi[RBLK], dot[RBLK];
+#pragma unroll
+                for (int u = 0; u < RBLK; ++u) {
+                    const int i = blk * RBLK + u;
+                    const bool ok = i > j && i < n;
+                    vk[u] = (ok && lane <= jp) ? __ldcg(jb.Vp + (size_t)i * NB + lane) : 0.f;
+                    wk[u] = (ok && lane < jp) ? __ldcg(jb.Wp + (size_t)i * NB + lane) : 0.f;
+                }
+                assemble_y(jb, blk, yi);
+#pragma unroll
+                for (int u = 0; u < RBLK; ++u) dot[u] = lane < jp ? vk[u] * sm.q[lane] + wk[u] * sm.q[32 + lane] : 0.f;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+                    for (int u = 0; u < RBLK; ++u) dot[u] += __shfl_xor_sync(0xffffffffu, dot[u], o);
+#pragma unroll
+                for (int u = 0; u < RBLK; ++u) {
+                    const int i = blk * RBLK + u;
+                    const float vlast = __shfl_sync(0xffffffffu, vk[u], jp);
+                    if (lane == jp && i > j && i < n) jb.Wp[(size_t)i * NB + lane] = tau_p * (yi[u] - dot[u]) - cw * vlast;
+                }
             }
             team_barrier(jb.bar, target, team);
             TRD_TICK(7);
@@ -472,14 +589,14 @@ static double job_time(int n, int team) {
     double bw = 60e9 * team;
     if (bw > 6.0e12) bw = 6.0e12;
     const double n2 = (double)n * n, n3 = n2 * n;
-    const double t_rows = (n2 / 2.0) / (16.0 * team) * 0.75e-6;
-    return n * t_fix + t_rows + (4.0 / 3.0) * n3 / bw + (4.0 / 3.0) * n3 / (150e9 * team);
+    const double t_rows = (n2 / 2.0) / (16.0 * 8.0 * team) * 1.5e-6;      // 8-row blocks, one after the other per warp
+    // product: lower triangle only, 2 m^2 bytes per column = 2/3 n^3 bytes; rank-2k updates: 4/3 n^3 flops
+    return n * t_fix + t_rows + (2.0 / 3.0) * n3 / bw + (4.0 / 3.0) * n3 / (300e9 * team);
 }
 
 int plan_teams(const int* n, int njobs, int sms, int* team, int* cta_begin, int* entries) {
     static int forced = -2;                                           // KFACB_TRD_TEAM=k: every job on a team of k (tuning aid)
     if (forced == -2) { const char* e = getenv("KFACB_TRD_TEAM"); forced = (e && *e) ? atoi(e) : -1; }
-    static const int cand[] = {1, 2, 3, 4, 6, 8, 12, 16, 24, 32, 48, 64, 96, 128, 1 << 30};
     struct TeamRec { int size; double load; int first_job, njobs; };
     int* order = new int[njobs];
     for (int i = 0; i < njobs; ++i) order[i] = i;
@@ -500,11 +617,8 @@ int plan_teams(const int* n, int njobs, int sms, int* team, int* cta_begin, int*
             const int jn = n[order[a]];
             int tsel = -1;
             if (forced > 0) tsel = forced > sms ? sms : forced;
-            else for (int c : cand) {
-                const int t = c > sms ? sms : c;
+            else for (int t = 1; t <= sms; ++t)                      // smallest team that meets the limit
                 if (job_time(jn, t) <= limit) { tsel = t; break; }
-                if (t == sms) break;
-            }
             if (tsel < 0) return false;
             const double jt = job_time(jn, tsel);
             int k = -1;

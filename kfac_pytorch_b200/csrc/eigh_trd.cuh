@@ -26,6 +26,7 @@ struct Job {
     float* x;             // n: column being reduced
     float* y;             // n: T v
     float* part;          // NPART x TS partial sums
+    float* zpart;         // team x ldt: every CTA's transposed contributions z (symmetric product from the lower triangle)
     unsigned* bar;        // team barrier counter (zero on entry)
     long long* prof;      // NULL, or 9 clock64 totals of the phases (debug: KFACB_TRD_PROF=1)
     int n, ldt, team;

@@ -225,7 +225,7 @@ def test_kfac_state_round_trip_resumes_bit_identically():
 
 def test_eigh_team_scheduler_is_sane_for_resnet50():
     """kfacb_eigh_plan_teams (no GPU needed): every n > 128 factor gets a team, the persistent kernel never asks for
-    more CTAs than the device has SMs, and the big factors get the big teams."""
+    more CTAs than the device has SMs, and the big factors get the big teams (n <= 64 takes the in-SMEM Jacobi path)."""
     from kfac_pytorch_b200 import native
     from kfac_pytorch_b200.workloads import layer_dims, resnet50_layers
     lib = native.load_library()
@@ -238,10 +238,10 @@ def test_eigh_team_scheduler_is_sane_for_resnet50():
         grid = lib.kfacb_eigh_plan_teams(arr, len(ns), sms, out)
         assert 0 < grid <= sms
         for n, t in zip(ns, out):
-            assert (t == 0) == (n <= 128) and t <= sms
+            assert (t == 0) == (n <= 64) and t <= sms
         big = max(t for n, t in zip(ns, out) if n == 4608)
         assert all(t <= big for t in out)
-    assert lib.kfacb_eigh_workspace_bytes(arr, len(ns)) > 4 * sum(4 * n * n for n in ns if n > 128)
+    assert lib.kfacb_eigh_workspace_bytes(arr, len(ns)) > 4 * sum(4 * n * n for n in ns if n > 64)
     lone = (ctypes.c_int32 * 1)(4608)
     out1 = (ctypes.c_int32 * 1)()
     assert lib.kfacb_eigh_plan_teams(lone, 1, 148, out1) == out1[0] >= 64      # a lone big factor gets most of the GPU
