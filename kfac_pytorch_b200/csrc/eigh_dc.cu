@@ -1070,12 +1070,16 @@ int eigh_tdc_run(const int32_t* n, const int* idx, int nb, const float* const* M
         std::vector<long long> hp((size_t)16 * nb);
         if (cudaStreamSynchronize(st) == cudaSuccess &&
             cudaMemcpy(hp.data(), zero + pl.z_prof, hp.size() * sizeof(long long), cudaMemcpyDeviceToHost) == cudaSuccess)
+        {
+            long long t0 = 0;
+            for (int a = 0; a < nb; ++a) { const long long s0 = hp[(size_t)16 * a + 9]; if (s0 && (!t0 || s0 < t0)) t0 = s0; }
             for (int a = 0; a < nb; ++a) {
                 const long long* q = hp.data() + 16 * a;
-                fprintf(stderr, "[kfacb trd profile] n=%d team=%d  kcycles: A_pro %lld A_rows %lld bar1 %lld B_setup %lld B_symv %lld "
-                        "B_red %lld bar2 %lld pan_fin %lld rank2k %lld\n", pl.ml[a].n, pl.team[a], q[0] / 1000, q[1] / 1000,
-                        q[2] / 1000, q[3] / 1000, q[4] / 1000, q[5] / 1000, q[6] / 1000, q[7] / 1000, q[8] / 1000);
+                fprintf(stderr, "[kfacb trd profile] n=%d team=%d  start %.2f end %.2f ms  kcycles: A_pro %lld A_rows %lld bar1 %lld B_setup %lld B_symv %lld "
+                        "B_red %lld bar2 %lld pan_fin %lld rank2k %lld\n", pl.ml[a].n, pl.team[a], (q[9] - t0) * 1e-6, (q[10] - t0) * 1e-6,
+                        q[0] / 1000, q[1] / 1000, q[2] / 1000, q[3] / 1000, q[4] / 1000, q[5] / 1000, q[6] / 1000, q[7] / 1000, q[8] / 1000);
             }
+        }
     }
     // ---- (2) divide and conquer ----
     static bool attr_done[64] = {false};

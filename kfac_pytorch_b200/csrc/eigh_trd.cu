@@ -21,6 +21,7 @@
 //   * reflector j is left in the dead row j of the work array (T[j][j+1..n)), K-contiguous, which is exactly the
 //     operand layout the tensor-core back-transformation (eigh_dc.cu) wants.
 // The formulas are pinned by tools/eigh_trd_dc_model.py (same phases in numpy).
+#include <math.h>
 #include <stdlib.h>
 #include <type_traits>
 #include "eigh_trd.cuh"
@@ -258,6 +259,7 @@ __device__ void run_job(const Job& jb, int rank, Smem& sm) {
     const bool prof_on = jb.prof != nullptr && rank == 0 && tid == 0;
     long long prof_acc[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
     long long t_last = prof_on ? clock64() : 0;
+    if (prof_on) { unsigned long long g; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(g)); jb.prof[9] = (long long)g; }
 #define TRD_TICK(slot) do { if (prof_on) { const long long now_ = clock64(); prof_acc[slot] += now_ - t_last; t_last = now_; } } while (0)
     for (int j = 0; j < n - 1; ++j) {
         const int jp = j - j0;
@@ -379,31 +381,63 @@ __device__ void run_job(const Job& jb, int rank, Smem& sm) {
             __syncthreads();
             const int q_hi = K > 0 ? 2 * (b_first + (K - 1) * team) + 1 : -1;                   // last quad of the longest block
             const int nchunk = q_hi >= q_beg ? (q_hi - q_beg) / 32 + 1 : 0;
-            for (int c0 = 0; c0 < nchunk; c0 += 2 * NWARP) {
-                for (int half = 0; half < 2; ++half) {
-                    const int c = c0 + (half == 0 ? warp : 2 * NWARP - 1 - warp);
-                    if (c >= nchunk) continue;
+            // Balanced dealing: the units (chunk c, block k >= kmin(c)) are numbered chunk-major and every warp takes a
+            // contiguous range of total / NWARP units -- equal work whatever the team size and n (a single-CTA team
+            // with n = 512 has 4 chunks but 128 units), and a warp's consecutive units mostly share the chunk, so
+            // the transposed half stays in registers and is flushed once per chunk (4 shared-memory atomics / lane).
+            // Lane l holds the unit counts of chunks l and l + 32 (nchunk <= MAXN / 128 = 64); warp-scan for the prefix.
+            const int qb2 = q_beg >> 1;
+            int km0, km1;
+            {
+                const int c0_ = lane, c1_ = lane + 32;
+                int t0 = (qb2 + 16 * c0_ - b_first + team - 1) / team; if (t0 < 0) t0 = 0;
+                int t1 = (qb2 + 16 * c1_ - b_first + team - 1) / team; if (t1 < 0) t1 = 0;
+                km0 = t0; km1 = t1;
+            }
+            const int w0 = (lane < nchunk && km0 < K) ? K - km0 : 0;
+            const int w1 = (lane + 32 < nchunk && km1 < K) ? K - km1 : 0;
+            int p0 = w0, p1 = w1;                                   // inclusive scans
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int a0 = __shfl_up_sync(0xffffffffu, p0, o), a1 = __shfl_up_sync(0xffffffffu, p1, o);
+                if (lane >= o) { p0 += a0; p1 += a1; }
+            }
+            const int tot0 = __shfl_sync(0xffffffffu, p0, 31);
+            p1 += tot0;
+            const int total = __shfl_sync(0xffffffffu, p1, 31);
+            const int u_lo = (int)(((long long)total * warp) / NWARP), u_hi = (int)(((long long)total * (warp + 1)) / NWARP);
+            if (u_hi > u_lo) {
+                // first chunk whose inclusive prefix exceeds u_lo
+                const unsigned b0m = __ballot_sync(0xffffffffu, p0 > u_lo), b1m = __ballot_sync(0xffffffffu, p1 > u_lo);
+                int c = b0m ? __ffs(b0m) - 1 : 32 + __ffs(b1m) - 1;
+                int u = u_lo;
+                while (u < u_hi) {
+                    const int src = c & 31;
+                    const int pin = c < 32 ? __shfl_sync(0xffffffffu, p0, src) : __shfl_sync(0xffffffffu, p1, src);
+                    const int wc = c < 32 ? __shfl_sync(0xffffffffu, w0, src) : __shfl_sync(0xffffffffu, w1, src);
+                    const int kmc = c < 32 ? __shfl_sync(0xffffffffu, km0, src) : __shfl_sync(0xffffffffu, km1, src);
+                    const int pst = pin - wc;                          // first unit of chunk c
+                    const int k_beg = kmc + (u - pst);
+                    const int u_end = pin < u_hi ? pin : u_hi;
+                    const int k_end = kmc + (u_end - pst);
                     const int q = q_beg + 32 * c + lane;
-                    // first block that reaches this chunk: 2 blk + 1 >= q_beg + 32 c
-                    int kmin = ((q_beg + 32 * c) / 2 - b_first + team - 1) / team;
-                    if (kmin < 0) kmin = 0;
                     const float4 vv = *reinterpret_cast<const float4*>(&sm.v[4 * (q < (ldt >> 2) ? q : q_beg)]);
                     float4 zc = make_float4(0.f, 0.f, 0.f, 0.f);
-                    for (int k = kmin; k < K; ++k) {
+                    for (int k = k_beg; k < k_end; ++k) {
                         const int i0 = (b_first + k * team) * RBLK;
                         float4 m[RBLK];
 #pragma unroll
-                        for (int u = 0; u < RBLK; ++u) {
-                            const int i = i0 + u;
-                            m[u] = (i > j && i < n && 4 * q <= i)
-                                       ? __ldcg(reinterpret_cast<const float4*>(jb.T + (size_t)i * ldt) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+                        for (int uu = 0; uu < RBLK; ++uu) {
+                            const int i = i0 + uu;
+                            m[uu] = (i > j && i < n && 4 * q <= i)
+                                        ? __ldcg(reinterpret_cast<const float4*>(jb.T + (size_t)i * ldt) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
                         }
                         float acc[RBLK];
                         const bool edge = 4 * q + 3 >= i0;            // this quad touches the diagonal of some row of the block
 #pragma unroll
-                        for (int u = 0; u < RBLK; ++u) {
-                            float4 t = m[u];
-                            const int i = i0 + u;
+                        for (int uu = 0; uu < RBLK; ++uu) {
+                            float4 t = m[uu];
+                            const int i = i0 + uu;
                             const float vi = (i > j && i < n) ? sm.v[i] : 0.f;
                             if (edge) {                               // c <= i for the row sum, c < i for the transposed half
                                 const int cc = 4 * q;
@@ -411,13 +445,13 @@ __device__ void run_job(const Job& jb, int rank, Smem& sm) {
                                 if (cc + 1 > i) t.y = 0.f;
                                 if (cc + 2 > i) t.z = 0.f;
                                 if (cc + 3 > i) t.w = 0.f;
-                                acc[u] = fmaf(t.x, vv.x, fmaf(t.y, vv.y, fmaf(t.z, vv.z, t.w * vv.w)));
+                                acc[uu] = fmaf(t.x, vv.x, fmaf(t.y, vv.y, fmaf(t.z, vv.z, t.w * vv.w)));
                                 if (cc == i) t.x = 0.f;
                                 if (cc + 1 == i) t.y = 0.f;
                                 if (cc + 2 == i) t.z = 0.f;
                                 if (cc + 3 == i) t.w = 0.f;
                             } else {
-                                acc[u] = fmaf(t.x, vv.x, fmaf(t.y, vv.y, fmaf(t.z, vv.z, t.w * vv.w)));
+                                acc[uu] = fmaf(t.x, vv.x, fmaf(t.y, vv.y, fmaf(t.z, vv.z, t.w * vv.w)));
                             }
                             zc.x = fmaf(t.x, vi, zc.x); zc.y = fmaf(t.y, vi, zc.y);
                             zc.z = fmaf(t.z, vi, zc.z); zc.w = fmaf(t.w, vi, zc.w);
@@ -425,16 +459,18 @@ __device__ void run_job(const Job& jb, int rank, Smem& sm) {
 #pragma unroll
                         for (int o = 16; o > 0; o >>= 1)
 #pragma unroll
-                            for (int u = 0; u < RBLK; ++u) acc[u] += __shfl_xor_sync(0xffffffffu, acc[u], o);
+                            for (int uu = 0; uu < RBLK; ++uu) acc[uu] += __shfl_xor_sync(0xffffffffu, acc[uu], o);
                         float mine = acc[0];
 #pragma unroll
-                        for (int u = 1; u < RBLK; ++u) if (lane == u) mine = acc[u];
+                        for (int uu = 1; uu < RBLK; ++uu) if (lane == uu) mine = acc[uu];
                         if (lane < RBLK) atomicAdd(&sm.ysum[k * RBLK + lane], mine);
                     }
                     if (q < (ldt >> 2)) {
                         atomicAdd(&sm.z[4 * q], zc.x); atomicAdd(&sm.z[4 * q + 1], zc.y);
                         atomicAdd(&sm.z[4 * q + 2], zc.z); atomicAdd(&sm.z[4 * q + 3], zc.w);
                     }
+                    u = u_end;
+                    ++c;
                 }
             }
             TRD_TICK(4);
@@ -525,8 +561,10 @@ __device__ void run_job(const Job& jb, int rank, Smem& sm) {
         }
     }
     if (rank == 0 && tid == 0) jb.d[n - 1] = __ldcg(jb.T + (size_t)(n - 1) * ldt + (n - 1));
-    if (prof_on)
+    if (prof_on) {
         for (int q = 0; q < 9; ++q) jb.prof[q] = prof_acc[q];
+        unsigned long long g; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(g)); jb.prof[10] = (long long)g;
+    }
 #undef TRD_TICK
     __syncthreads();
 }
@@ -580,18 +618,19 @@ __global__ void trd_copy_kernel(const Job* jobs, const float* const* src) {
 // ---------------------------------------------------------------------------
 // host: team sizes and the per-CTA schedule
 // ---------------------------------------------------------------------------
-// Cost model of one job on a team (seconds), calibrated on B200 with KFACB_TRD_PROF / KFACB_TRD_TEAM
-// (profiles/r02_trd_calibration.txt): per column two team barriers (~1.6 us each) + the latency-bound short phases;
-// rows handled one warp-batch after the other (matters for small teams); the product streams 4 m^2 bytes per
-// column at ~60 GB/s per SM up to the HBM / L2 ceiling; the rank-2k updates do 4/3 n^3 flops at ~150 GFLOP/s per SM.
+// Cost model of one job on a team (seconds), fitted to B200 measurements of single matrices on forced team sizes
+// (tools/trd_calib.py, profiles/r02_trd_calibration.txt; n = 256 .. 4608, teams 1 .. 147, all points within 6 %):
+//   per column: the dependent chain of short phases + two team barriers -- 9.7 us on a single CTA, 11.6 us on teams
+//               up to 16, + 1.5 us per doubling beyond (barrier fan-in, slowest-member wait);
+//   row phases (finish w, form the column, publish y / the reflector): 20 ns per (row, column) pair / team;
+//   symmetric product: 2/3 n^3 bytes at 48.6 GB/s per SM (16 warps x 4 KB in flight) up to the HBM ceiling (113 SMs);
+//   rank-2k updates: 4/3 n^3 flops at 150 GFLOP/s per SM.
 static double job_time(int n, int team) {
-    const double t_fix = team > 1 ? 7.5e-6 : 4.5e-6;
-    double bw = 60e9 * team;
-    if (bw > 6.0e12) bw = 6.0e12;
+    double f = team > 1 ? 11.6e-6 : 9.7e-6;
+    if (team > 16) f += 1.5e-6 * log2((double)team / 16.0);
     const double n2 = (double)n * n, n3 = n2 * n;
-    const double t_rows = (n2 / 2.0) / (16.0 * 8.0 * team) * 1.5e-6;      // 8-row blocks, one after the other per warp
-    // product: lower triangle only, 2 m^2 bytes per column = 2/3 n^3 bytes; rank-2k updates: 4/3 n^3 flops
-    return n * t_fix + t_rows + (2.0 / 3.0) * n3 / bw + (4.0 / 3.0) * n3 / (300e9 * team);
+    const double tp = team < 113 ? team : 113;
+    return n * f + 0.0201e-6 * n2 / team + 1.37e-11 * n3 / tp + 0.89e-11 * n3 / team;
 }
 
 int plan_teams(const int* n, int njobs, int sms, int* team, int* cta_begin, int* entries) {

@@ -188,13 +188,19 @@ class NativeEngine:
         return torch.cuda.current_stream(self.device).cuda_stream
 
     # -- (1) factors -------------------------------------------------------
-    def factor_update(self, layers, a, g, A, G, alpha: float, first_step: bool):
+    def factor_update(self, layers, a, g, A, G, alpha: float, first_step: bool, workspace_key: str = 'factor'):
+        """a[i] / g[i] (and the matching A[i] / G[i]) may be None: that side of layer i is skipped."""
         for t in list(a) + list(g) + list(A) + list(G):
-            _check_f32(t, 'factor_update operand')
+            if t is not None:
+                _check_f32(t, 'factor_update operand')
         d = _descs(layers)
         n = len(layers)
         nbytes = self.lib.kfacb_factor_workspace_bytes(d, n)
-        ws = self._workspace('factor', nbytes)
+        cur = self._ws.get(workspace_key)
+        if workspace_key != 'factor' and cur is not None and cur.numel() < nbytes:
+            # a side-stream workspace may still be in use by the previous launch: drain that stream before it is replaced
+            torch.cuda.current_stream(self.device).synchronize()
+        ws = self._workspace(workspace_key, nbytes)
         with torch.cuda.device(self.device):
             self._call(self.lib.kfacb_factor_update(d, n, _ptrs(a), _ptrs(g), _ptrs(A), _ptrs(G),
                                                     alpha, int(first_step), ws.data_ptr(),

@@ -118,7 +118,8 @@ class KFAC(optim.Optimizer):
     def __init__(self, model, lr=0.1, damping=0.001, fac_update_freq=1, kfac_update_freq=1,
                  kl_clip=0.001, factor_decay=0.95, exclude_vocabulary_size=None,
                  hook_enabled=True, exclude_parts='', *, partition='round_robin', engine=None,
-                 communicate_inverse_or_not=False, distribute_layer_factors=None):
+                 communicate_inverse_or_not=False, distribute_layer_factors=None,
+                 overlap_factor_capture=False):
         defaults = dict(lr=lr, damping=damping, fac_update_freq=fac_update_freq,
                         kfac_update_freq=kfac_update_freq)
         super().__init__(model.parameters(), defaults)
@@ -142,6 +143,12 @@ class KFAC(optim.Optimizer):
         self.exclude_communicate_factor = exclude_parts.find('CommunicateFactor') >= 0
         self.exclude_compute_factor = exclude_parts.find('ComputeFactor') >= 0
         self.partition = partition
+        # launch each layer's factor accumulation from its own forward / backward hook on a side
+        # stream, so the SYRKs overlap the rest of the forward / backward pass and the captured activations are
+        # released as soon as their kernel has run (keyword-only; DP variants; not part of the reference signature)
+        self.overlap_factor_capture = bool(overlap_factor_capture)
+        self._cap_stream = None
+        self._cap_done = {'a': set(), 'g': set()}
 
         self.modules: List[torch.nn.Module] = []
         self.module_names: List[str] = []
@@ -185,7 +192,10 @@ class KFAC(optim.Optimizer):
                 return
             rank_a, _ = self.module_ranks[module]
             if backend.comm.rank() == rank_a:
-                self.m_a[module] = input[0].data
+                if self._overlap_active():
+                    self._capture_now(module, 'a', input[0].data)
+                else:
+                    self.m_a[module] = input[0].data
 
     def _backward_hook_event(self, module, grad_input, grad_output):
         """Owner-only capture of the output gradient (kfac_preconditioner_inv_dp.py:67-72)."""
@@ -195,7 +205,43 @@ class KFAC(optim.Optimizer):
                 return
             _, rank_g = self.module_ranks[module]
             if backend.comm.rank() == rank_g:
-                self.m_g[module] = grad_output[0].data
+                if self._overlap_active():
+                    self._capture_now(module, 'g', grad_output[0].data)
+                else:
+                    self.m_g[module] = grad_output[0].data
+
+    # -------------------------------------------- overlapped capture (8f rank 1)
+    def _overlap_active(self) -> bool:
+        return (self.overlap_factor_capture and self.is_dp and not self.exclude_compute_factor
+                and self.modules[0].weight.device.type == 'cuda')
+
+    def _capture_now(self, module, which: str, t: torch.Tensor):
+        """Factor accumulation of ONE layer side ('a' -> A at forward time, 'g' -> G at backward time) launched
+        from the hook on the capture stream: same kernel, same EMA / identity-init flags as ``_compute_factors``
+        (kfac_preconditioner_inv_dp.py:60-90), only earlier and off the main stream.  The captured tensor is not
+        retained: ``record_stream`` keeps its memory alive until the kernel has consumed it."""
+        if module in self._cap_done[which]:
+            raise RuntimeError('overlap_factor_capture=True needs exactly one forward/backward per step(): %s was '
+                               'captured twice (gradient accumulation re-applies the running average; use the '
+                               'default capture mode for that)' % self.module_names[self.modules.index(module)])
+        eng = self._get_engine()
+        dev = t.device
+        if self._cap_stream is None:
+            self._cap_stream = torch.cuda.Stream(device=dev)
+        t = _prep(t)
+        d = _full_desc(module, t if which == 'a' else None, t if which == 'g' else None)
+        store, n = (self.m_A, d.dA) if which == 'a' else (self.m_G, d.dG)
+        if module not in store:
+            mk = torch.empty if self.steps == 0 else (lambda k, _k, **kw: torch.eye(k, **kw))
+            store[module] = mk(n, n, dtype=torch.float32, device=dev)
+        side = self._cap_stream
+        side.wait_stream(torch.cuda.current_stream(dev))      # the tensor (and a fresh factor buffer) are ready
+        with torch.cuda.stream(side):
+            eng.factor_update([d], [t if which == 'a' else None], [t if which == 'g' else None],
+                              [store[module] if which == 'a' else None], [store[module] if which == 'g' else None],
+                              self.factor_decay, self.steps == 0, workspace_key='factor_capture')
+        t.record_stream(side)
+        self._cap_done[which].add(module)
 
     def _register_module_hooks(self, model):
         """Class-NAME match on {'Linear','Conv2d'} in model.modules() order
@@ -275,11 +321,24 @@ class KFAC(optim.Optimizer):
         local mini-batch (kfac_preconditioner_inv_dp.py:75-90)."""
         eng = self._get_engine()
         owned = self._owned() if self.is_dp else list(range(len(self.modules)))   # MPD: full replicas (inv.py:80-91)
+        if self._cap_stream is not None and (self._cap_done['a'] or self._cap_done['g']):
+            # overlapped capture: the hooks already launched these layers' SYRKs; join the capture stream
+            torch.cuda.current_stream(self._device()).wait_stream(self._cap_stream)
+            done = self._cap_done
+            missing = [i for i in owned if (self.modules[i] in done['a']) != (self.modules[i] in done['g'])]
+            if missing:
+                raise RuntimeError('overlap_factor_capture: layer %s saw only one of its forward / backward hooks '
+                                   'this step' % self.module_names[missing[0]])
+            owned = [i for i in owned if self.modules[i] not in done['a']]
+            self._cap_done = {'a': set(), 'g': set()}
         if not owned:
             return
         descs, a_l, g_l, A_l, G_l = [], [], [], [], []
         for i in owned:
             m = self.modules[i]
+            if m not in self.m_a or m not in self.m_g:
+                raise RuntimeError('%s: no captured input / output gradient for this step (run forward + backward with '
+                                   'the hooks enabled, or inject m_a / m_g)' % self.module_names[i])
             a, g = _prep(self.m_a[m]), _prep(self.m_g[m])
             d = _full_desc(m, a, g)
             if m not in self.m_A:

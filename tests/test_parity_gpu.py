@@ -152,3 +152,54 @@ def test_exclude_parts_and_frequency_gating_on_device():
     for b, p in zip(before, model.parameters()):
         assert torch.equal(b, p.grad)
     assert len(pre.m_A) == 2 and pre.steps == 1
+
+
+def _conv_net(dev):
+    torch.manual_seed(3)
+    return torch.nn.Sequential(
+        torch.nn.Conv2d(3, 16, 3, padding=1), torch.nn.ReLU(),
+        torch.nn.Conv2d(16, 32, 3, stride=2, padding=1, bias=False), torch.nn.ReLU(),
+        torch.nn.AdaptiveAvgPool2d(1), torch.nn.Flatten(), torch.nn.Linear(32, 10)).to(dev)
+
+
+@pytest.mark.parametrize('variant', ['eigen_dp', 'inverse_dp'])
+def test_overlapped_factor_capture_matches_deferred_capture(variant):
+    """factor accumulation launched from the hooks on a side stream (overlap_factor_capture=True)
+    gives the same factors and the same rewritten gradients as the reference's capture-then-accumulate-in-step()
+    order (kfac_preconditioner_inv_dp.py:60-90), over several steps incl. the identity-initialised first one, and does
+    not retain the captured tensors."""
+    import kfac_pytorch_b200 as kfac
+    from kfac_pytorch_b200 import backend
+    backend.comm = None
+    dev = torch.device('cuda:0')
+    out = {}
+    for overlap in (False, True):
+        model = _conv_net(dev)
+        pre = kfac.get_kfac_module(variant)(model, lr=0.1, damping=0.03, kl_clip=0.001, overlap_factor_capture=overlap)
+        gen = torch.Generator(device=dev).manual_seed(11)
+        for s in range(3):
+            x = torch.randn(8, 3, 12, 12, device=dev, generator=gen)
+            y = torch.randint(0, 10, (8,), device=dev, generator=gen)
+            model.zero_grad()
+            torch.nn.functional.cross_entropy(model(x), y).backward()
+            if overlap:
+                assert pre.m_a == {} and pre.m_g == {}          # nothing retained: the SYRKs were launched from the hooks
+            pre.step()
+        out[overlap] = ([pre.m_A[m].clone() for m in pre.modules] + [pre.m_G[m].clone() for m in pre.modules],
+                        [p.grad.clone() for p in model.parameters()])
+    for a, b in zip(out[False][0] + out[False][1], out[True][0] + out[True][1]):
+        assert torch.allclose(a, b, rtol=1e-6, atol=1e-8), (a - b).abs().max().item()
+
+
+def test_overlapped_factor_capture_refuses_gradient_accumulation():
+    import kfac_pytorch_b200 as kfac
+    from kfac_pytorch_b200 import backend
+    backend.comm = None
+    dev = torch.device('cuda:0')
+    model = _conv_net(dev)
+    pre = kfac.DP_KFAC(model, overlap_factor_capture=True)
+    x = torch.randn(4, 3, 12, 12, device=dev)
+    model(x).sum().backward()
+    with pytest.raises(RuntimeError, match='exactly one forward/backward'):
+        model(x).sum().backward()
+    assert pre.steps == 0
