@@ -37,6 +37,7 @@ struct __align__(16) Smem {
     float ysum[MAXN];                                           // row sums of the CTA's own blocks: [8 k + u] = row u of its k-th owned block
     float op[4][NB][OP_PITCH];                                  // rank-2k update operands: V_I, W_I, W_J, V_J (k-major)
     float red[3][NWARP][33];
+    float qraw[72];                                             // team sums of the raw (unscaled) panel inner products, [64] = |x|^2
     float q[72];                                                // team-reduced partial sums: [0,32) W^T v, [32,64) V^T v, [64] v.y, [65] |x|^2
     float rowV[32], rowW[32];
     float cw, tau, scale;
@@ -70,72 +71,51 @@ __device__ __forceinline__ int first_block(int r0, int rank, int team) {
     return b0 + o;
 }
 
-// Team-wide sums of the partial sums of the last product pass + what finishing column `kc` of W needs.
-// Quantity k lives in part[k * TS + rank]; one warp adds the team's slots of a quantity (coalesced, fixed order:
-// identical bits on every CTA); only the kc live panel columns of s = W^T v (q[0..)) and t = V^T v (q[32..)) are
-// read; every load of a warp is issued before the first reduction.  Then warp 0 forms
-// cw = tau^2 (v.y - 2 s.t) / 2 and, with want_row, finishes W[row_j][kc] redundantly (every CTA needs row j of the
-// panels) and stages rows j of V and W -- its loads of row j were issued together with the partial sums.
-// All threads; ends with a barrier.
-__device__ __forceinline__ void reduce_and_prologue(const Job& jb, Smem& sm, int kc, int row_j, bool want_row) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    float vj = 0.f, wj = 0.f, yj = 0.f;
-    if (warp == 0 && want_row) {
-        vj = lane <= kc ? __ldcg(jb.Vp + (size_t)row_j * NB + lane) : 0.f;
-        wj = lane < kc ? __ldcg(jb.Wp + (size_t)row_j * NB + lane) : 0.f;
-        // y_j = own lower-triangle part + every CTA's transposed contributions to row j
-        float zz = 0.f;
+// Start of a column (after the product's barrier): cw = tau^2 (v.y - 2 s.t) / 2 from the team-summed v.y and the
+// panel inner products s = W^T v (sm.q[0..)), t = V^T v (sm.q[32..)) that B_setup already reduced; with want_row,
+// warp 0 also finishes W[row_j][kc] redundantly (every CTA needs row j of the panels) and stages rows j of V and W.
+// The loads are issued by `prologue_issue` BEFORE the caller issues its own row loads, so both round trips overlap.
+struct ProRegs { float vy, vj, wj, zz, yj; };
+__device__ __forceinline__ void prologue_issue(const Job& jb, int kc, int row_j, bool want_row, ProRegs& r) {
+    const int lane = threadIdx.x & 31;
+    r.vy = 0.f; r.vj = 0.f; r.wj = 0.f; r.zz = 0.f; r.yj = 0.f;
 #pragma unroll
-        for (int it = 0; it < TS / 32; ++it) {
-            const int r = lane + 32 * it;
-            if (r < jb.team) zz += __ldcg(jb.zpart + (size_t)r * jb.ldt + row_j);
-        }
-        yj = __ldcg(jb.y + row_j) + warp_sum(zz);
-    }
-    constexpr int PER = (65 + NWARP - 1) / NWARP;               // quantities per warp
-    float a[PER];
-#pragma unroll
-    for (int u = 0; u < PER; ++u) {
-        const int k = warp + NWARP * u;
-        a[u] = 0.f;
-        const bool live = k < 65 && (k == 64 || (k & 31) < kc);
-        if (live) {
-#pragma unroll
-            for (int it = 0; it < TS / 32; ++it) {               // fixed trip count: every load of the warp is in flight at once
-                const int r = lane + 32 * it;
-                if (r < jb.team) a[u] += __ldcg(jb.part + k * TS + r);
-            }
+    for (int it = 0; it < TS / 32; ++it) {
+        const int q = lane + 32 * it;
+        if (q < jb.team) {
+            r.vy += __ldcg(jb.part + 64 * TS + q);
+            if (want_row) r.zz += __ldcg(jb.zpart + (size_t)q * jb.ldt + row_j);
         }
     }
-#pragma unroll
-    for (int u = 0; u < PER; ++u) {
-        const int k = warp + NWARP * u;
-        const float t = warp_sum(a[u]);
-        if (lane == 0 && k < 65) sm.q[k] = t;
+    if (want_row) {
+        r.vj = lane <= kc ? __ldcg(jb.Vp + (size_t)row_j * NB + lane) : 0.f;
+        r.wj = lane < kc ? __ldcg(jb.Wp + (size_t)row_j * NB + lane) : 0.f;
+        r.yj = __ldcg(jb.y + row_j);
     }
-    __syncthreads();
-    if (warp == 0) {
-        const float s = sm.q[lane], t = sm.q[32 + lane], vy = sm.q[64];
-        const float st = warp_sum(lane < kc ? s * t : 0.f);
-        const float tau = sm.tau;
-        const float cw = 0.5f * tau * tau * (vy - 2.f * st);
-        if (lane == 0) sm.cw = cw;
-        if (want_row) {
-            const float dot = warp_sum(lane < kc ? vj * s + wj * t : 0.f);
-            const float vlast = __shfl_sync(0xffffffffu, vj, kc);
-            const float wnew = tau * (yj - dot) - cw * vlast;
-            if (lane == kc) wj = wnew;
-            sm.rowV[lane] = vj;
-            sm.rowW[lane] = wj;
-        }
+}
+// warp 0 only; the caller synchronises the CTA afterwards
+__device__ __forceinline__ void prologue_finish(Smem& sm, int kc, bool want_row, const ProRegs& r) {
+    const int lane = threadIdx.x & 31;
+    const float vy = warp_sum(r.vy);
+    const float s = sm.q[lane], t = sm.q[32 + lane];
+    const float st = warp_sum(lane < kc ? s * t : 0.f);
+    const float tau = sm.tau;
+    const float cw = 0.5f * tau * tau * (vy - 2.f * st);
+    if (lane == 0) sm.cw = cw;
+    if (want_row) {
+        const float yj = r.yj + warp_sum(r.zz);
+        const float dot = warp_sum(lane < kc ? r.vj * s + r.wj * t : 0.f);
+        const float vlast = __shfl_sync(0xffffffffu, r.vj, kc);
+        const float wnew = tau * (yj - dot) - cw * vlast;
+        sm.rowV[lane] = r.vj;
+        sm.rowW[lane] = lane == kc ? wnew : r.wj;
     }
-    __syncthreads();
 }
 
 // A[R0.., R0..] -= V W^T + W V^T over the first kc panel columns; tiles of 128x128 dealt to the team.
 // 16 warps = 4 x 4, lanes = 4 (row groups of 8) x 8 (column groups of 4): 8x4 outputs per thread; per k a warp
 // reads 6 shared-memory wavefronts (broadcast within a group) for 64 FMAs -> FMA bound.
-__device__ void rank2k_update(const Job& jb, Smem& sm, int R0, int kc, int rank) {
+__device__ __noinline__ void rank2k_update(const Job& jb, Smem& sm, int R0, int kc, int rank) {
     const int n = jb.n, ldt = jb.ldt;
     const int mt = n - R0;
     if (mt <= 0) return;
@@ -169,6 +149,15 @@ __device__ void rank2k_update(const Job& jb, Smem& sm, int R0, int kc, int rank)
                 for (int u = 0; u < 4; ++u) sm.op[o][4 * kq + u][r] = (4 * kq + u < kc) ? a[o][u] : 0.f;
         }
         __syncthreads();
+        // the old values of the tile are requested BEFORE the k loop: their L2 / HBM round trip hides behind the FMAs
+        const int gc = R0 + 128 * tj + col4;
+        const bool vec = aligned && gc + 3 < n;
+        float4 c[8];
+#pragma unroll
+        for (int a = 0; a < 8; ++a) {
+            const int gi = R0 + 128 * ti + row8 + a;
+            c[a] = (vec && gi < n) ? __ldcg(reinterpret_cast<const float4*>(jb.T + (size_t)gi * ldt + gc)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
         float acc[8][4];
 #pragma unroll
         for (int a = 0; a < 8; ++a)
@@ -189,15 +178,7 @@ __device__ void rank2k_update(const Job& jb, Smem& sm, int R0, int kc, int rank)
 #pragma unroll
                 for (int b = 0; b < 4; ++b) acc[a][b] = fmaf(va[a], wb[b], fmaf(wa[a], vb[b], acc[a][b]));
         }
-        const int gc = R0 + 128 * tj + col4;
-        if (aligned && gc + 3 < n) {
-            // all eight old rows in flight before the first store (a store may alias the next load for the compiler)
-            float4 c[8];
-#pragma unroll
-            for (int a = 0; a < 8; ++a) {
-                const int gi = R0 + 128 * ti + row8 + a;
-                c[a] = gi < n ? __ldcg(reinterpret_cast<const float4*>(jb.T + (size_t)gi * ldt + gc)) : make_float4(0.f, 0.f, 0.f, 0.f);
-            }
+        if (vec) {
 #pragma unroll
             for (int a = 0; a < 8; ++a) {
                 const int gi = R0 + 128 * ti + row8 + a;
@@ -263,15 +244,16 @@ __device__ void run_job(const Job& jb, int rank, Smem& sm) {
 #define TRD_TICK(slot) do { if (prof_on) { const long long now_ = clock64(); prof_acc[slot] += now_ - t_last; t_last = now_; } } while (0)
     for (int j = 0; j < n - 1; ++j) {
         const int jp = j - j0;
-        // ---------------- phase A: finish w_{j-1} (rows >= j), form column j and |x|^2 ----------------
-        if (jp > 0) reduce_and_prologue(jb, sm, jp - 1, j, true);
-        TRD_TICK(0);
+        // ---------------- phase A: finish w_{j-1} (rows >= j), form column j, |x|^2 and the raw panel inner products ----
+        // s = W^T v and t = V^T v of THIS column are linear in v = (x with x_{j+1} -> 1) * scale, and the panel rows
+        // are in registers here anyway: the sums over rows >= j+2 of W[i][k] x_i, V[i][k] x_i ride on the |x|^2 barrier
+        // (B_setup applies `scale` and adds row j+1), so the product phase needs no second pass over the panels.
         {
-            const float tau_p = sm.tau, cw = sm.cw;
-            float nrm = 0.f;
-            // one 8-row block per warp iteration: all loads of the block are issued before the first reduction
-            for (int blk = first_block(j, rank, team) + team * warp; blk * RBLK < n; blk += team * NWARP) {
-                float vk[RBLK], wk[RBLK], yi[RBLK], tji[RBLK];
+            ProRegs pr;
+            if (jp > 0 && warp == 0) prologue_issue(jb, jp - 1, j, true, pr);
+            const int blk0 = first_block(j, rank, team) + team * warp;
+            float vk[RBLK], wk[RBLK], tji[RBLK], yi[RBLK];
+            auto load_block = [&](int blk) {
 #pragma unroll
                 for (int u = 0; u < RBLK; ++u) {
                     const int i = blk * RBLK + u;
@@ -280,8 +262,19 @@ __device__ void run_job(const Job& jb, int rank, Smem& sm) {
                     wk[u] = (ok && lane < jp - 1) ? __ldcg(jb.Wp + (size_t)i * NB + lane) : 0.f;
                     tji[u] = ok ? __ldcg(jb.T + (size_t)j * ldt + i) : 0.f;
                 }
+                if (jp > 0) assemble_y(jb, blk, yi);
+            };
+            if (blk0 * RBLK < n) load_block(blk0);
+            if (jp > 0) {
+                if (warp == 0) prologue_finish(sm, jp - 1, true, pr);
+                __syncthreads();
+            }
+            TRD_TICK(0);
+            const float tau_p = sm.tau, cw = sm.cw;
+            float nrm = 0.f, sraw = 0.f, traw = 0.f;
+            for (int blk = blk0; blk * RBLK < n; blk += team * NWARP) {
+                if (blk != blk0) load_block(blk);
                 if (jp > 0) {
-                    assemble_y(jb, blk, yi);
                     float dot[RBLK];
 #pragma unroll
                     for (int u = 0; u < RBLK; ++u) dot[u] = lane < jp - 1 ? vk[u] * sm.q[lane] + wk[u] * sm.q[32 + lane] : 0.f;
@@ -308,18 +301,25 @@ __device__ void run_job(const Job& jb, int rank, Smem& sm) {
                 for (int u = 0; u < RBLK; ++u) {
                     const int i = blk * RBLK + u;
                     const float xi = tji[u] - corr[u];
+                    if (i >= j + 2 && i < n) {                          // lane k: column k of the panels
+                        sraw = fmaf(wk[u], xi, sraw);
+                        traw = fmaf(vk[u], xi, traw);
+                    }
                     if (lane == 0 && i >= j && i < n) {
                         if (i == j) jb.d[j] = xi;
                         else { jb.x[i] = xi; if (i >= j + 2) nrm = fmaf(xi, xi, nrm); }
                     }
                 }
             }
-            if (lane == 0) sm.red[0][warp][0] = nrm;
+            sm.red[0][warp][lane] = sraw;
+            sm.red[1][warp][lane] = traw;
+            if (lane == 0) sm.red[2][warp][0] = nrm;
             __syncthreads();
-            if (tid == 0) {
-                float tot = 0.f;
-                for (int w = 0; w < NWARP; ++w) tot += sm.red[0][w][0];
-                jb.part[65 * TS + rank] = tot;
+            if (warp == 0) {
+                float ss = 0.f, tt = 0.f, tot = 0.f;
+                for (int w = 0; w < NWARP; ++w) { ss += sm.red[0][w][lane]; tt += sm.red[1][w][lane]; tot += sm.red[2][w][0]; }
+                if (lane < jp) { jb.part[lane * TS + rank] = ss; jb.part[(32 + lane) * TS + rank] = tt; }
+                if (lane == 0) jb.part[65 * TS + rank] = tot;
             }
         }
         TRD_TICK(1);
@@ -334,28 +334,60 @@ __device__ void run_job(const Job& jb, int rank, Smem& sm) {
             const int c = c_al + tid + u * THREADS;
             xr[u] = (c > j + 1 && c < n) ? __ldcg(jb.x + c) : 0.f;
         }
-        if (warp == 0) {
-            float s2 = 0.f;
+        {
+            // team sums of |x|^2 (quantity 64 here) and of the raw panel inner products (k < jp and 32 + k, k < jp):
+            // one warp per quantity, every load of a warp issued before its first reduction, fixed order
+            constexpr int PER = (65 + NWARP - 1) / NWARP;
+            float a[PER];
 #pragma unroll
-            for (int it = 0; it < TS / 32; ++it) {
-                const int r = lane + 32 * it;
-                if (r < team) s2 += __ldcg(jb.part + 65 * TS + r);
+            for (int u = 0; u < PER; ++u) {
+                const int k = warp + NWARP * u;
+                a[u] = 0.f;
+                const bool live = k < 65 && (k == 64 || (k & 31) < jp);
+                const int row = k == 64 ? 65 : k;
+                if (live) {
+#pragma unroll
+                    for (int it = 0; it < TS / 32; ++it) {
+                        const int r = lane + 32 * it;
+                        if (r < team) a[u] += __ldcg(jb.part + row * TS + r);
+                    }
+                }
             }
-            s2 = warp_sum(s2);
-            const float alpha = __ldcg(jb.x + j + 1);
-            float beta, tau, scale;
-            if (s2 == 0.f) { tau = 0.f; beta = alpha; scale = 0.f; }
-            else {
-                beta = -copysignf(sqrtf(fmaf(alpha, alpha, s2)), alpha);
-                tau = (beta - alpha) / beta;
-                scale = 1.f / (alpha - beta);
+            // row j+1 of the panels (its v is exactly 1) and alpha
+            float w1 = 0.f, v1 = 0.f, alpha = 0.f;
+            if (warp == 1) {
+                w1 = lane < jp ? __ldcg(jb.Wp + (size_t)(j + 1) * NB + lane) : 0.f;
+                v1 = lane < jp ? __ldcg(jb.Vp + (size_t)(j + 1) * NB + lane) : 0.f;
             }
-            if (lane == 0) {
-                sm.tau = tau; sm.scale = scale;
-                if (rank == 0) { jb.e[j] = beta; jb.tau[j] = tau; }
+            if (warp == 0) alpha = __ldcg(jb.x + j + 1);
+#pragma unroll
+            for (int u = 0; u < PER; ++u) {
+                const int k = warp + NWARP * u;
+                const float t = warp_sum(a[u]);
+                if (lane == 0 && k < 65) sm.qraw[k] = t;
+            }
+            __syncthreads();
+            if (warp == 0) {
+                const float s2 = sm.qraw[64];
+                float beta, tau, scale;
+                if (s2 == 0.f) { tau = 0.f; beta = alpha; scale = 0.f; }
+                else {
+                    beta = -copysignf(sqrtf(fmaf(alpha, alpha, s2)), alpha);
+                    tau = (beta - alpha) / beta;
+                    scale = 1.f / (alpha - beta);
+                }
+                if (lane == 0) {
+                    sm.tau = tau; sm.scale = scale;
+                    if (rank == 0) { jb.e[j] = beta; jb.tau[j] = tau; }
+                }
+            }
+            __syncthreads();
+            if (warp == 1) {
+                const float scale = sm.scale;
+                sm.q[lane] = lane < jp ? fmaf(scale, sm.qraw[lane], w1) : 0.f;
+                sm.q[32 + lane] = lane < jp ? fmaf(scale, sm.qraw[32 + lane], v1) : 0.f;
             }
         }
-        __syncthreads();
         {
             const float scale = sm.scale;
 #pragma unroll
@@ -475,51 +507,31 @@ __device__ void run_job(const Job& jb, int rank, Smem& sm) {
             }
             TRD_TICK(4);
             __syncthreads();                                       // row sums and z complete
-            // per owned row: publish the own part of y, the reflector, and the panel inner products
-            float acc_s = 0.f, acc_t = 0.f, acc_vy = 0.f;
+            // per owned row: publish the own part of y and the reflector (lane u < 8 takes row u of the block)
+            float acc_vy = 0.f;
             for (int k = warp; k < K; k += NWARP) {
-                const int i0 = (b_first + k * team) * RBLK;
-                float wpi[RBLK], vpi[RBLK];
-#pragma unroll
-                for (int u = 0; u < RBLK; ++u) {                      // all panel rows of the block in flight before the stores
-                    const int i = i0 + u;
-                    const bool ok = i > j && i < n && lane < jp;
-                    wpi[u] = ok ? __ldcg(jb.Wp + (size_t)i * NB + lane) : 0.f;
-                    vpi[u] = ok ? __ldcg(jb.Vp + (size_t)i * NB + lane) : 0.f;
-                }
-#pragma unroll
-                for (int u = 0; u < RBLK; ++u) {
-                    const int i = i0 + u;
-                    if (i <= j || i >= n) continue;
-                    const float vi = sm.v[i], yl = sm.ysum[k * RBLK + u];
-                    acc_s = fmaf(wpi[u], vi, acc_s);
-                    acc_t = fmaf(vpi[u], vi, acc_t);
-                    if (lane == 0) {
-                        jb.y[i] = yl;                                  // own (lower-triangle) part of y_i
-                        acc_vy = fmaf(vi, yl, acc_vy);
-                        jb.Vp[(size_t)i * NB + jp] = vi;
-                        jb.T[(size_t)j * ldt + i] = vi;
-                    }
+                const int i = (b_first + k * team) * RBLK + lane;
+                if (lane < RBLK && i > j && i < n) {
+                    const float vi = sm.v[i], yl = sm.ysum[k * RBLK + lane];
+                    jb.y[i] = yl;                                      // own (lower-triangle) part of y_i
+                    acc_vy = fmaf(vi, yl, acc_vy);
+                    jb.Vp[(size_t)i * NB + jp] = vi;
+                    jb.T[(size_t)j * ldt + i] = vi;
                 }
             }
             // hand z to the team (coalesced) and fold its share of v.y:  v.y = sum_i v_i ylow_i + sum_c v_c z_c
-            float vz = 0.f;
             for (int c = c_al + tid; c < ldt; c += THREADS) {
                 const float zc = sm.z[c];
                 jb.zpart[(size_t)rank * ldt + c] = zc;
-                vz = fmaf(sm.v[c], zc, vz);
+                acc_vy = fmaf(sm.v[c], zc, acc_vy);
             }
-            vz = warp_sum(vz);
-            sm.red[0][warp][lane] = acc_s;
-            sm.red[1][warp][lane] = acc_t;
-            if (lane == 0) sm.red[2][warp][0] = acc_vy + vz;
+            acc_vy = warp_sum(acc_vy);
+            if (lane == 0) sm.red[2][warp][0] = acc_vy;
             __syncthreads();
-            if (warp == 0) {
-                float s = 0.f, t = 0.f, vy = 0.f;
-                for (int w = 0; w < NWARP; ++w) { s += sm.red[0][w][lane]; t += sm.red[1][w][lane]; vy += sm.red[2][w][0]; }
-                jb.part[lane * TS + rank] = s;
-                jb.part[(32 + lane) * TS + rank] = t;
-                if (lane == 0) jb.part[64 * TS + rank] = vy;
+            if (tid == 0) {
+                float vy = 0.f;
+                for (int w = 0; w < NWARP; ++w) vy += sm.red[2][w][0];
+                jb.part[64 * TS + rank] = vy;
             }
         }
         TRD_TICK(5);
@@ -527,7 +539,11 @@ __device__ void run_job(const Job& jb, int rank, Smem& sm) {
         TRD_TICK(6);
         // ---------------- panel end: finish w_j (rows > j), rank-2k update of the trailing square ----------------
         if (jp == NB - 1 || j == n - 2) {
-            reduce_and_prologue(jb, sm, jp, 0, false);
+            {
+                ProRegs pr;
+                if (warp == 0) { prologue_issue(jb, jp, 0, false, pr); prologue_finish(sm, jp, false, pr); }
+                __syncthreads();
+            }
             const float tau_p = sm.tau, cw = sm.cw;
             for (int blk = first_block(j + 1, rank, team) + team * warp; blk * RBLK < n; blk += team * NWARP) {
                 float vk[RBLK], wk[RBLK], yi[RBLK], dot[RBLK];

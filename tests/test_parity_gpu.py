@@ -187,8 +187,13 @@ def test_overlapped_factor_capture_matches_deferred_capture(variant):
             pre.step()
         out[overlap] = ([pre.m_A[m].clone() for m in pre.modules] + [pre.m_G[m].clone() for m in pre.modules],
                         [p.grad.clone() for p in model.parameters()])
-    for a, b in zip(out[False][0] + out[False][1], out[True][0] + out[True][1]):
-        assert torch.allclose(a, b, rtol=1e-6, atol=1e-8), (a - b).abs().max().item()
+    # the factors come from the same kernel on the same data (only the batching of the launch differs: split-K
+    # shapes may change the summation order); the rewritten gradients go through eigh / the inverse on top of that
+    for a, b in zip(out[False][0], out[True][0]):
+        assert torch.allclose(a, b, rtol=1e-5, atol=1e-7), (a - b).abs().max().item()
+    for a, b in zip(out[False][1], out[True][1]):
+        e = ((a - b).norm() / b.norm().clamp_min(1e-30)).item()
+        assert e < 1e-4, e
 
 
 def test_overlapped_factor_capture_refuses_gradient_accumulation():
