@@ -268,6 +268,38 @@ int    kfacb_finalize_grads(const kfacb_layer_t* layers, int32_t count,
                             void* workspace, size_t workspace_bytes,
                             kfacb_stream_t stream);
 
+/* ---------------------------------------------------------------------------
+ * (4b) Split finalize + gradient packing: the pieces of the FUSED gradient-reduce
+ * path (reduce-to-owner -> precondition -> exchange instead of the caller's
+ * all-reduce followed by step(); examples/pytorch_imagenet_resnet.py:371-383 and
+ * kfac_preconditioner_inv.py:188-217).
+ *
+ *   kfacb_pack_grads     dst[i] <- [wgrad[i] (dG x dW) | bgrad[i] (dG)], contiguous: the
+ *                        send buffer of the reduce-to-owner; a segment of that buffer is
+ *                        afterwards handed to kfacb_precond_* as wgrad / bgrad pointers.
+ *   kfacb_finalize_dot   vg_sum_out[0] = sum over the GIVEN layers of sum(v * grad)
+ *                        (double, fixed order, no lr^2): an owner's partial of the KL-clip
+ *                        sum, to be summed across ranks by the caller (one 8-byte
+ *                        all-reduce).
+ *   kfacb_finalize_write nu from the GLOBAL vg_sum (device double[1]) exactly like
+ *                        kfacb_finalize_grads, then the in-place rewrite of every layer.
+ * workspace: kfacb_finalize_workspace_bytes(layers, count) for all three.
+ * ------------------------------------------------------------------------- */
+int    kfacb_pack_grads(const kfacb_layer_t* layers, int32_t count,
+                        const float* const* wgrad, const float* const* bgrad, float* const* dst,
+                        void* workspace, size_t workspace_bytes, kfacb_stream_t stream);
+int    kfacb_finalize_dot(const kfacb_layer_t* layers, int32_t count,
+                          const float* const* precon,
+                          const float* const* wgrad, const float* const* bgrad,
+                          double* vg_sum_out,
+                          void* workspace, size_t workspace_bytes, kfacb_stream_t stream);
+int    kfacb_finalize_write(const kfacb_layer_t* layers, int32_t count,
+                            const float* const* precon,
+                            float* const* wgrad, float* const* bgrad,
+                            const double* vg_sum, float lr, float kl_clip, int32_t force_nu_one,
+                            float* nu_out,
+                            void* workspace, size_t workspace_bytes, kfacb_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

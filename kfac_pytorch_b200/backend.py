@@ -103,6 +103,9 @@ class _SingleBackend(_BackendBase):
     def broadcast_async_(self, tensor, src, group=None, name=None):
         return None
 
+    def reduce_async_(self, tensor, dst, op=Ops.Average):
+        return None
+
     def synchronize(self, handle):
         return None
 
@@ -139,6 +142,16 @@ class _TorchBackend(_BackendBase):
 
     def broadcast_async_(self, tensor, src, group=None, name=None):
         return dist.broadcast(tensor, src=src, group=group, async_op=True)
+
+    def reduce_async_(self, tensor, dst, op=Ops.Average):
+        """Reduce-to-owner (not in the reference backend: the fused gradient-reduce path).
+        NCCL averages on the wire; gloo (CPU tests) sums and the destination divides."""
+        if op == Ops.Average and dist.get_backend() == 'nccl':
+            return dist.reduce(tensor, dst=dst, op=dist.ReduceOp.AVG, async_op=True)
+        handle = dist.reduce(tensor, dst=dst, op=dist.ReduceOp.SUM, async_op=True)
+        if op == Ops.Average and self.rank() == dst:
+            return (handle, tensor)
+        return handle
 
     def synchronize(self, handle):
         if handle is None:

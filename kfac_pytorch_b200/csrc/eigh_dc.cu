@@ -781,7 +781,7 @@ struct Plan {
     // offsets inside the workspace
     size_t off_tables = 0, off_zero = 0, zero_bytes = 0, off_mats = 0, total = 0;
     size_t t_jobs = 0, t_mats = 0, t_src = 0, t_oidx = 0, t_wpre = 0, t_cta = 0, t_ent = 0, t_leaves = 0, t_merges = 0, t_gemm = 0,
-           t_panels = 0, t_y = 0, t_yt = 0, t_upd = 0, tables_bytes = 0;
+           t_panels = 0, t_y = 0, t_yt = 0, t_upd = 0, t_tmaps = 0, tables_bytes = 0;
     size_t z_bar = 0, z_states = 0, z_prof = 0;
 };
 
@@ -889,6 +889,7 @@ static void build_plan(const int32_t* n, const int* idx, int nb, Plan& pl) {
     pl.t_y = ttake(sizeof(Tile) * (pl.y_tiles.size() + 1));
     pl.t_yt = ttake(sizeof(Tile) * (pl.yt_tiles.size() + 1));
     pl.t_upd = ttake(sizeof(Tile) * (pl.upd_tiles.size() + 1));
+    pl.t_tmaps = ttake((size_t)128 * (nb + 1));      // CUtensorMap of every work array (TMA-fed symmetric product)
     pl.tables_bytes = t;
     pl.off_tables = take(t);
     // ---- zero-initialised block: barrier counters (one 128-byte line each), merge states ----
@@ -945,7 +946,8 @@ int eigh_tdc_last_profile(double* out8) {
     if (cudaEventElapsedTime(&t, s->ev[0], s->ev[1]) == cudaSuccess) out8[0] = t;      // tridiagonalisation (copy + persistent kernel)
     if (cudaEventElapsedTime(&t, s->ev[1], s->ev[2]) == cudaSuccess) out8[1] = t;      // divide and conquer
     if (cudaEventElapsedTime(&t, s->ev[2], s->ev[3]) == cudaSuccess) out8[2] = t;      // back-transformation + write
-    out8[3] = s->bytes_trd;     // algorithmic bytes of the tridiagonalisation: sum 4/3 n^3 (one read of the trailing matrix per column)
+    out8[3] = s->bytes_trd;     // algorithmic bytes of the tridiagonalisation: sum (2/3 + 1/12) n^3 -- the lower triangle of the trailing
+                                // matrix read once per column (symmetric product) + one read-modify-write of it per 32-column panel
     out8[4] = s->n3;            // sum n^3 of the blocked matrices
     out8[5] = s->nb; out8[6] = s->grid;
     (void)cudaGetLastError();
@@ -1011,6 +1013,11 @@ int eigh_tdc_run(const int32_t* n, const int* idx, int nb, const float* const* M
         jb.bar = reinterpret_cast<unsigned*>(zero + pl.z_bar + (size_t)128 * a);
         jb.n = m.n; jb.ldt = m.ldz; jb.team = pl.team[a];
         jb.prof = trd_prof ? reinterpret_cast<long long*>(zero + pl.z_prof) + 16 * a : nullptr;
+        jb.tmap = ws + pl.off_tables + pl.t_tmaps + (size_t)128 * a;
+        {
+            const int er = trd::encode_tmap(img.data() + pl.t_tmaps + (size_t)128 * a, jb.T, m.n, m.ldz);
+            KFACB_REQUIRE(er == 0, "cuTensorMapEncodeTiled failed (%d) for matrix %d (n = %d)", er, idx[a], m.n);
+        }
         DcMat& mt = mats[a];
         mt.T = jb.T; mt.Z[0] = reinterpret_cast<float*>(ws + m.Z0); mt.Z[1] = reinterpret_cast<float*>(ws + m.Z1);
         mt.U = reinterpret_cast<float*>(ws + m.U); mt.Ypart = reinterpret_cast<float*>(ws + m.Ypart);
@@ -1058,13 +1065,15 @@ int eigh_tdc_run(const int32_t* n, const int* idx, int nb, const float* const* M
     StageEvents* sev = stage_events();
     if (sev) {
         sev->nb = nb; sev->grid = pl.grid; sev->bytes_trd = 0; sev->n3 = 0;
-        for (int a = 0; a < nb; ++a) { const double n3 = (double)pl.ml[a].n * pl.ml[a].n * pl.ml[a].n; sev->n3 += n3; sev->bytes_trd += 4.0 / 3.0 * n3; }
+        for (int a = 0; a < nb; ++a) { const double n3 = (double)pl.ml[a].n * pl.ml[a].n * pl.ml[a].n; sev->n3 += n3; sev->bytes_trd += 0.75 * n3; }
         cudaEventRecord(sev->ev[0], st);
     }
     // ---- (1) tridiagonalisation ----
     KFACB_CHECK_CUDA(trd::launch_copy(d_jobs, reinterpret_cast<const float* const*>(tb + pl.t_src), nb, pl.nmax, st));
+    size_t trd_smem = 0;
+    for (int a = 0; a < nb; ++a) trd_smem = std::max(trd_smem, trd::smem_bytes(pl.ml[a].n, pl.team[a]));
     KFACB_CHECK_CUDA(trd::launch(d_jobs, reinterpret_cast<const int*>(tb + pl.t_cta),
-                                 reinterpret_cast<const int*>(tb + pl.t_ent), pl.grid, st));
+                                 reinterpret_cast<const int*>(tb + pl.t_ent), pl.grid, trd_smem, st));
     if (sev) cudaEventRecord(sev->ev[1], st);
     if (trd_prof) {
         std::vector<long long> hp((size_t)16 * nb);
@@ -1076,8 +1085,9 @@ int eigh_tdc_run(const int32_t* n, const int* idx, int nb, const float* const* M
             for (int a = 0; a < nb; ++a) {
                 const long long* q = hp.data() + 16 * a;
                 fprintf(stderr, "[kfacb trd profile] n=%d team=%d  start %.2f end %.2f ms  kcycles: A_pro %lld A_rows %lld bar1 %lld B_setup %lld B_symv %lld "
-                        "B_red %lld bar2 %lld pan_fin %lld rank2k %lld\n", pl.ml[a].n, pl.team[a], (q[9] - t0) * 1e-6, (q[10] - t0) * 1e-6,
-                        q[0] / 1000, q[1] / 1000, q[2] / 1000, q[3] / 1000, q[4] / 1000, q[5] / 1000, q[6] / 1000, q[7] / 1000, q[8] / 1000);
+                        "B_red %lld bar2 %lld pan_fin %lld rank2k %lld | warp 0: tma_wait %lld units %lld\n", pl.ml[a].n, pl.team[a], (q[9] - t0) * 1e-6, (q[10] - t0) * 1e-6,
+                        q[0] / 1000, q[1] / 1000, q[2] / 1000, q[3] / 1000, q[4] / 1000, q[5] / 1000, q[6] / 1000, q[7] / 1000, q[8] / 1000,
+                        q[11] / 1000, q[12]);
             }
         }
     }

@@ -22,28 +22,63 @@
 //     operand layout the tensor-core back-transformation (eigh_dc.cu) wants.
 // The formulas are pinned by tools/eigh_trd_dc_model.py (same phases in numpy).
 #include <math.h>
+#include <cuda.h>
 #include <stdlib.h>
+#include <string.h>
 #include <type_traits>
 #include "eigh_trd.cuh"
 
 namespace kfacb {
 namespace trd {
 
+constexpr int RBLK8 = 8;                                         // rows per block (see RBLK below)
 constexpr int OP_PITCH = 132;                                   // 128 + 4: float4-aligned, spreads banks
+constexpr int NSLOT = 2;                                        // product ring: slots per warp
+constexpr int SLOT_BYTES = RBLK8 * 512;                          // one unit = 8 rows x 128 columns
+constexpr int RING_BYTES = NWARP * NSLOT * SLOT_BYTES;          // 128 KB
 
-struct __align__(16) Smem {
-    float v[MAXN];                                              // reflector of the current column (absolute index)
-    float z[MAXN];                                              // this CTA's transposed contributions  z_c = sum_{own rows i > c} T[i][c] v_i
-    float ysum[MAXN];                                           // row sums of the CTA's own blocks: [8 k + u] = row u of its k-th owned block
-    float op[4][NB][OP_PITCH];                                  // rank-2k update operands: V_I, W_I, W_J, V_J (k-major)
+// Fixed part of the dynamic shared memory; followed by the per-job vectors  v[ldt] | z[ldt] | ysum[ycap]:
+//   v     reflector of the current column (absolute index)
+//   z     this CTA's transposed contributions  z_c = sum_{own rows i > c} T[i][c] v_i
+//   ysum  row sums of the CTA's own blocks: [8 k + u] = row u of its k-th owned block
+struct __align__(128) Smem {
+    unsigned char ring[RING_BYTES];                             // operands of the symmetric product, filled by TMA bulk copies
+                                                                // (per warp NSLOT x 4 KB); the rank-2k operands alias it
     float red[3][NWARP][33];
     float qraw[72];                                             // team sums of the raw (unscaled) panel inner products, [64] = |x|^2
-    float q[72];                                                // team-reduced partial sums: [0,32) W^T v, [32,64) V^T v, [64] v.y, [65] |x|^2
+    float q[72];                                                // panel inner products of the current reflector: [0,32) W^T v, [32,64) V^T v
     float rowV[32], rowW[32];
     float cw, tau, scale;
+    unsigned long long mbar[NWARP][NSLOT];                      // completion barriers of the ring slots
 };
+static_assert(sizeof(float) * 4 * NB * OP_PITCH <= RING_BYTES, "the rank-2k operands alias the product ring");
+constexpr int SMEM_LIMIT = 232448 - 1024;                       // 227 KB per CTA on sm_100, minus the static shared memory (the job descriptor)
+
+#ifdef TRD_EXPERIMENT_NO_ATOMICS
+#define SMEM_ADD(p, v) (*(p) += (v))
+#else
+#define SMEM_ADD(p, v) atomicAdd((p), (v))
+#endif
+// ---- TMA bulk copy (cp.async.bulk, SASS UBLKCP) + mbarrier transaction counting ----
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, uint32_t bytes) {
+    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+// one request = one 8-row x 128-column box of T (4 KB) -> row-major in the slot; out-of-range rows / columns arrive as zeros
+__device__ __forceinline__ void tma_box_g2s(void* dst, const void* tmap, int col, int row, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 ::"r"(smem_addr(dst)), "l"(tmap), "r"(col), "r"(row), "r"(smem_addr(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_parity(unsigned long long* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tWAIT_%=:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@p bra DONE_%=;\n\tbra WAIT_%=;\n\tDONE_%=:\n\t}\n"
+        ::"r"(smem_addr(bar)), "r"(parity) : "memory");
+}
+// generic-proxy writes to global memory (rank-2k update) before later async-proxy (TMA) reads of the same locations
+__device__ __forceinline__ void fence_proxy_async_global() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
 
 __device__ __forceinline__ void team_barrier(unsigned* ctr, unsigned& target, int team) {
+    fence_proxy_async_global();                                  // this thread's global writes vs. later TMA reads (any CTA of the team)
     __syncthreads();
     if (team > 1) {
         target += (unsigned)team;
@@ -63,12 +98,36 @@ __device__ __forceinline__ void team_barrier(unsigned* ctr, unsigned& target, in
 // Rows are dealt to the team in BLOCKS of 8 consecutive rows (block b -> CTA b mod team): the 8 rows of a block have
 // the same length in the lower triangle (one warp streams them together, 8 loads in flight per lane) and their
 // slice of any per-row vector is one 32-byte sector.  First block owned by `rank` that contains a row >= r0:
-constexpr int RBLK = 8;
+constexpr int RBLK = RBLK8;
 __device__ __forceinline__ int first_block(int r0, int rank, int team) {
     const int b0 = r0 >> 3;
     int o = rank - b0 % team;
     if (o < 0) o += team;
     return b0 + o;
+}
+
+// Sum of 8 per-lane values over the 32 lanes of a warp, all 8 at once: each of the exchanges over lane bits 4, 3, 2
+// halves the number of rows a lane carries (it sends the half it gives up), two more butterflies finish the one row
+// left.  9 shuffles instead of 40.  On return the lanes with (lane & 3) == 0 hold the total of row (lane >> 2).
+__device__ __forceinline__ float row_reduce8(const float (&a)[8]) {
+    const int lane = threadIdx.x & 31;
+    const bool h16 = lane & 16, h8 = lane & 8, h4 = lane & 4;
+    float b[4], c[2];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+        const float send = h16 ? a[u] : a[u + 4], keep = h16 ? a[u + 4] : a[u];
+        b[u] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+        const float send = h8 ? b[u] : b[u + 2], keep = h8 ? b[u + 2] : b[u];
+        c[u] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+    }
+    const float send = h4 ? c[0] : c[1], keep = h4 ? c[1] : c[0];
+    float r = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+    r += __shfl_xor_sync(0xffffffffu, r, 2);
+    r += __shfl_xor_sync(0xffffffffu, r, 1);
+    return r;
 }
 
 // Start of a column (after the product's barrier): cw = tau^2 (v.y - 2 s.t) / 2 from the team-summed v.y and the
@@ -124,6 +183,7 @@ __device__ __noinline__ void rank2k_update(const Job& jb, Smem& sm, int R0, int 
     const int row8 = 32 * (warp >> 2) + 8 * (lane >> 3);
     const int col4 = 32 * (warp & 3) + 4 * (lane & 7);
     const bool aligned = (R0 & 3) == 0;
+    float (*op)[NB][OP_PITCH] = reinterpret_cast<float (*)[NB][OP_PITCH]>(sm.ring);
     for (int q = rank; q < nt * nt; q += jb.team) {
         const int ti = q / nt, tj = q - ti * nt;
         __syncthreads();
@@ -146,7 +206,7 @@ __device__ __noinline__ void rank2k_update(const Job& jb, Smem& sm, int R0, int 
 #pragma unroll
             for (int o = 0; o < 4; ++o)
 #pragma unroll
-                for (int u = 0; u < 4; ++u) sm.op[o][4 * kq + u][r] = (4 * kq + u < kc) ? a[o][u] : 0.f;
+                for (int u = 0; u < 4; ++u) op[o][4 * kq + u][r] = (4 * kq + u < kc) ? a[o][u] : 0.f;
         }
         __syncthreads();
         // the old values of the tile are requested BEFORE the k loop: their L2 / HBM round trip hides behind the FMAs
@@ -164,12 +224,12 @@ __device__ __noinline__ void rank2k_update(const Job& jb, Smem& sm, int R0, int 
 #pragma unroll
             for (int b = 0; b < 4; ++b) acc[a][b] = 0.f;
         for (int k = 0; k < kc; ++k) {
-            const float4 av0 = *reinterpret_cast<const float4*>(&sm.op[0][k][row8]);
-            const float4 av1 = *reinterpret_cast<const float4*>(&sm.op[0][k][row8 + 4]);
-            const float4 aw0 = *reinterpret_cast<const float4*>(&sm.op[1][k][row8]);
-            const float4 aw1 = *reinterpret_cast<const float4*>(&sm.op[1][k][row8 + 4]);
-            const float4 bw = *reinterpret_cast<const float4*>(&sm.op[2][k][col4]);
-            const float4 bv = *reinterpret_cast<const float4*>(&sm.op[3][k][col4]);
+            const float4 av0 = *reinterpret_cast<const float4*>(&op[0][k][row8]);
+            const float4 av1 = *reinterpret_cast<const float4*>(&op[0][k][row8 + 4]);
+            const float4 aw0 = *reinterpret_cast<const float4*>(&op[1][k][row8]);
+            const float4 aw1 = *reinterpret_cast<const float4*>(&op[1][k][row8 + 4]);
+            const float4 bw = *reinterpret_cast<const float4*>(&op[2][k][col4]);
+            const float4 bv = *reinterpret_cast<const float4*>(&op[3][k][col4]);
             const float va[8] = {av0.x, av0.y, av0.z, av0.w, av1.x, av1.y, av1.z, av1.w};
             const float wa[8] = {aw0.x, aw0.y, aw0.z, aw0.w, aw1.x, aw1.y, aw1.z, aw1.w};
             const float wb[4] = {bw.x, bw.y, bw.z, bw.w}, vb[4] = {bv.x, bv.y, bv.z, bv.w};
@@ -229,16 +289,48 @@ __device__ __forceinline__ void assemble_y(const Job& jb, int blk, float (&y8)[R
     for (int u = 0; u < RBLK; ++u) y8[u] = yo[u] + s[u];
 }
 
-__device__ void run_job(const Job& jb, int rank, Smem& sm) {
+// Per-lane partial of y_i for the 8 rows of block `blk` (no cross-lane reduction): lane l carries the transposed
+// contributions of CTAs r = l, l + 32, ..; lane 0 also carries the own lower-triangle part jb.y.
+__device__ __forceinline__ void partial_y(const Job& jb, int blk, float (&s)[RBLK]) {
+    const int lane = threadIdx.x & 31;
+    float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0;
+    const int i0 = blk * RBLK;
+#pragma unroll
+    for (int it = 0; it < TS / 32; ++it) {
+        const int r = lane + 32 * it;
+        if (r < jb.team) {
+            const float4* z = reinterpret_cast<const float4*>(jb.zpart + (size_t)r * jb.ldt + i0);
+            const float4 z0 = __ldcg(z), z1 = __ldcg(z + 1);
+            a0.x += z0.x; a0.y += z0.y; a0.z += z0.z; a0.w += z0.w;
+            a1.x += z1.x; a1.y += z1.y; a1.z += z1.z; a1.w += z1.w;
+        }
+    }
+    if (lane == 0) {
+        const float4* yl = reinterpret_cast<const float4*>(jb.y + i0);
+        const float4 y0 = __ldcg(yl), y1 = __ldcg(yl + 1);
+        a0.x += y0.x; a0.y += y0.y; a0.z += y0.z; a0.w += y0.w;
+        a1.x += y1.x; a1.y += y1.y; a1.z += y1.z; a1.w += y1.w;
+    }
+    s[0] = a0.x; s[1] = a0.y; s[2] = a0.z; s[3] = a0.w; s[4] = a1.x; s[5] = a1.y; s[6] = a1.z; s[7] = a1.w;
+}
+
+__device__ void run_job(const Job& jb, int rank, Smem& sm, float* dynf, uint32_t& ring_par) {
     const int n = jb.n, ldt = jb.ldt, team = jb.team;
+    float* const smv = dynf;
+    float* const smz = dynf + ldt;
+    float* const smy = dynf + 2 * ldt;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     unsigned target = 0;
     int j0 = 0;
-    if (tid == 0) sm.tau = 0.f;
+    if (tid == 0) {
+        sm.tau = 0.f;
+        asm volatile("prefetch.tensormap [%0];" ::"l"(jb.tmap) : "memory");   // descriptor into the TMA unit's cache
+    }
     __syncthreads();
     // optional phase profile (KFACB_TRD_PROF=1): clock64 deltas of thread 0 of the team's first CTA
     const bool prof_on = jb.prof != nullptr && rank == 0 && tid == 0;
     long long prof_acc[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    long long prof_wait = 0, prof_units = 0;                     // warp 0: cycles spent waiting for TMA data / units consumed
     long long t_last = prof_on ? clock64() : 0;
     if (prof_on) { unsigned long long g; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(g)); jb.prof[9] = (long long)g; }
 #define TRD_TICK(slot) do { if (prof_on) { const long long now_ = clock64(); prof_acc[slot] += now_ - t_last; t_last = now_; } } while (0)
@@ -262,7 +354,7 @@ __device__ void run_job(const Job& jb, int rank, Smem& sm) {
                     wk[u] = (ok && lane < jp - 1) ? __ldcg(jb.Wp + (size_t)i * NB + lane) : 0.f;
                     tji[u] = ok ? __ldcg(jb.T + (size_t)j * ldt + i) : 0.f;
                 }
-                if (jp > 0) assemble_y(jb, blk, yi);
+                if (jp > 0) partial_y(jb, blk, yi);                  // per-lane partials; reduced together with the panel dot
             };
             if (blk0 * RBLK < n) load_block(blk0);
             if (jp > 0) {
@@ -275,32 +367,27 @@ __device__ void run_job(const Job& jb, int rank, Smem& sm) {
             for (int blk = blk0; blk * RBLK < n; blk += team * NWARP) {
                 if (blk != blk0) load_block(blk);
                 if (jp > 0) {
-                    float dot[RBLK];
+                    float e[RBLK];                                     // per-lane partial of y_i - (V s + W t)_i
 #pragma unroll
-                    for (int u = 0; u < RBLK; ++u) dot[u] = lane < jp - 1 ? vk[u] * sm.q[lane] + wk[u] * sm.q[32 + lane] : 0.f;
-#pragma unroll
-                    for (int o = 16; o > 0; o >>= 1)
-#pragma unroll
-                        for (int u = 0; u < RBLK; ++u) dot[u] += __shfl_xor_sync(0xffffffffu, dot[u], o);
+                    for (int u = 0; u < RBLK; ++u) e[u] = yi[u] - (lane < jp - 1 ? vk[u] * sm.q[lane] + wk[u] * sm.q[32 + lane] : 0.f);
+                    const float r = row_reduce8(e);                   // lane 4 u: row u
 #pragma unroll
                     for (int u = 0; u < RBLK; ++u) {
                         const int i = blk * RBLK + u;
+                        const float ydu = __shfl_sync(0xffffffffu, r, 4 * u);
                         const float vlast = __shfl_sync(0xffffffffu, vk[u], jp - 1);
-                        const float wnew = tau_p * (yi[u] - dot[u]) - cw * vlast;
+                        const float wnew = tau_p * ydu - cw * vlast;
                         if (lane == jp - 1 && i >= j && i < n) { wk[u] = wnew; jb.Wp[(size_t)i * NB + lane] = wnew; }
                     }
                 }
                 float corr[RBLK];
 #pragma unroll
                 for (int u = 0; u < RBLK; ++u) corr[u] = lane < jp ? vk[u] * sm.rowW[lane] + wk[u] * sm.rowV[lane] : 0.f;
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1)
-#pragma unroll
-                    for (int u = 0; u < RBLK; ++u) corr[u] += __shfl_xor_sync(0xffffffffu, corr[u], o);
+                const float rc = row_reduce8(corr);                   // lane 4 u: row u
 #pragma unroll
                 for (int u = 0; u < RBLK; ++u) {
                     const int i = blk * RBLK + u;
-                    const float xi = tji[u] - corr[u];
+                    const float xi = tji[u] - __shfl_sync(0xffffffffu, rc, 4 * u);
                     if (i >= j + 2 && i < n) {                          // lane k: column k of the panels
                         sraw = fmaf(wk[u], xi, sraw);
                         traw = fmaf(vk[u], xi, traw);
@@ -334,66 +421,34 @@ __device__ void run_job(const Job& jb, int rank, Smem& sm) {
             const int c = c_al + tid + u * THREADS;
             xr[u] = (c > j + 1 && c < n) ? __ldcg(jb.x + c) : 0.f;
         }
-        {
-            // team sums of |x|^2 (quantity 64 here) and of the raw panel inner products (k < jp and 32 + k, k < jp):
-            // one warp per quantity, every load of a warp issued before its first reduction, fixed order
-            constexpr int PER = (65 + NWARP - 1) / NWARP;
-            float a[PER];
+        if (warp == 0) {
+            float s2 = 0.f;
 #pragma unroll
-            for (int u = 0; u < PER; ++u) {
-                const int k = warp + NWARP * u;
-                a[u] = 0.f;
-                const bool live = k < 65 && (k == 64 || (k & 31) < jp);
-                const int row = k == 64 ? 65 : k;
-                if (live) {
-#pragma unroll
-                    for (int it = 0; it < TS / 32; ++it) {
-                        const int r = lane + 32 * it;
-                        if (r < team) a[u] += __ldcg(jb.part + row * TS + r);
-                    }
-                }
+            for (int it = 0; it < TS / 32; ++it) {
+                const int r = lane + 32 * it;
+                if (r < team) s2 += __ldcg(jb.part + 65 * TS + r);
             }
-            // row j+1 of the panels (its v is exactly 1) and alpha
-            float w1 = 0.f, v1 = 0.f, alpha = 0.f;
-            if (warp == 1) {
-                w1 = lane < jp ? __ldcg(jb.Wp + (size_t)(j + 1) * NB + lane) : 0.f;
-                v1 = lane < jp ? __ldcg(jb.Vp + (size_t)(j + 1) * NB + lane) : 0.f;
+            const float alpha = __ldcg(jb.x + j + 1);
+            s2 = warp_sum(s2);
+            float beta, tau, scale;
+            if (s2 == 0.f) { tau = 0.f; beta = alpha; scale = 0.f; }
+            else {
+                beta = -copysignf(sqrtf(fmaf(alpha, alpha, s2)), alpha);
+                tau = (beta - alpha) / beta;
+                scale = 1.f / (alpha - beta);
             }
-            if (warp == 0) alpha = __ldcg(jb.x + j + 1);
-#pragma unroll
-            for (int u = 0; u < PER; ++u) {
-                const int k = warp + NWARP * u;
-                const float t = warp_sum(a[u]);
-                if (lane == 0 && k < 65) sm.qraw[k] = t;
-            }
-            __syncthreads();
-            if (warp == 0) {
-                const float s2 = sm.qraw[64];
-                float beta, tau, scale;
-                if (s2 == 0.f) { tau = 0.f; beta = alpha; scale = 0.f; }
-                else {
-                    beta = -copysignf(sqrtf(fmaf(alpha, alpha, s2)), alpha);
-                    tau = (beta - alpha) / beta;
-                    scale = 1.f / (alpha - beta);
-                }
-                if (lane == 0) {
-                    sm.tau = tau; sm.scale = scale;
-                    if (rank == 0) { jb.e[j] = beta; jb.tau[j] = tau; }
-                }
-            }
-            __syncthreads();
-            if (warp == 1) {
-                const float scale = sm.scale;
-                sm.q[lane] = lane < jp ? fmaf(scale, sm.qraw[lane], w1) : 0.f;
-                sm.q[32 + lane] = lane < jp ? fmaf(scale, sm.qraw[32 + lane], v1) : 0.f;
+            if (lane == 0) {
+                sm.tau = tau; sm.scale = scale;
+                if (rank == 0) { jb.e[j] = beta; jb.tau[j] = tau; }
             }
         }
+        __syncthreads();
         {
             const float scale = sm.scale;
 #pragma unroll
             for (int u = 0; u < XR; ++u) {
                 const int c = c_al + tid + u * THREADS;
-                if (c < ldt) { sm.v[c] = (c == j + 1) ? 1.f : xr[u] * scale; sm.z[c] = 0.f; }
+                if (c < ldt) { smv[c] = (c == j + 1) ? 1.f : xr[u] * scale; smz[c] = 0.f; }
             }
         }
         __syncthreads();
@@ -409,7 +464,7 @@ __device__ void run_job(const Job& jb, int rank, Smem& sm) {
             const int q_beg = c_al >> 2;
             const int b_first = first_block(j + 1, rank, team);
             const int K = b_first * RBLK < n ? ((n - 1) / RBLK - b_first) / team + 1 : 0;      // owned blocks this column
-            for (int e = tid; e < K * RBLK; e += THREADS) sm.ysum[e] = 0.f;
+            for (int e = tid; e < K * RBLK; e += THREADS) smy[e] = 0.f;
             __syncthreads();
             const int q_hi = K > 0 ? 2 * (b_first + (K - 1) * team) + 1 : -1;                   // last quad of the longest block
             const int nchunk = q_hi >= q_beg ? (q_hi - q_beg) / 32 + 1 : 0;
@@ -439,38 +494,105 @@ __device__ void run_job(const Job& jb, int rank, Smem& sm) {
             const int total = __shfl_sync(0xffffffffu, p1, 31);
             const int u_lo = (int)(((long long)total * warp) / NWARP), u_hi = (int)(((long long)total * (warp + 1)) / NWARP);
             if (u_hi > u_lo) {
-                // first chunk whose inclusive prefix exceeds u_lo
+                // Unit iterators over the warp's range (warp-uniform): `pi` runs NSLOT units ahead of `ci` and issues
+                // the TMA copy of a unit (ONE tensor-map request: the 8 x 128 box of T) into ring slot (unit & 1);
+                // the warp then waits on the slot's mbarrier, reads its quads from shared memory and, once the values
+                // are consumed, refills the slot.  Bytes in flight are bounded by the ring (8 KB / warp), not registers.
+                struct It { int c, k, k_end, u; };
                 const unsigned b0m = __ballot_sync(0xffffffffu, p0 > u_lo), b1m = __ballot_sync(0xffffffffu, p1 > u_lo);
-                int c = b0m ? __ffs(b0m) - 1 : 32 + __ffs(b1m) - 1;
-                int u = u_lo;
-                while (u < u_hi) {
+                const int c_first = b0m ? __ffs(b0m) - 1 : 32 + __ffs(b1m) - 1;
+                auto seek = [&](It& it, int c) {                       // position `it` on its unit it.u inside chunk c
                     const int src = c & 31;
                     const int pin = c < 32 ? __shfl_sync(0xffffffffu, p0, src) : __shfl_sync(0xffffffffu, p1, src);
                     const int wc = c < 32 ? __shfl_sync(0xffffffffu, w0, src) : __shfl_sync(0xffffffffu, w1, src);
                     const int kmc = c < 32 ? __shfl_sync(0xffffffffu, km0, src) : __shfl_sync(0xffffffffu, km1, src);
-                    const int pst = pin - wc;                          // first unit of chunk c
-                    const int k_beg = kmc + (u - pst);
+                    const int pst = pin - wc;
                     const int u_end = pin < u_hi ? pin : u_hi;
-                    const int k_end = kmc + (u_end - pst);
-                    const int q = q_beg + 32 * c + lane;
-                    const float4 vv = *reinterpret_cast<const float4*>(&sm.v[4 * (q < (ldt >> 2) ? q : q_beg)]);
-                    float4 zc = make_float4(0.f, 0.f, 0.f, 0.f);
-                    for (int k = k_beg; k < k_end; ++k) {
-                        const int i0 = (b_first + k * team) * RBLK;
+                    it.c = c; it.k = kmc + (it.u - pst); it.k_end = kmc + (u_end - pst);
+                };
+                auto advance = [&](It& it) {
+                    ++it.u; ++it.k;
+                    while (it.k >= it.k_end && it.u < u_hi) seek(it, it.c + 1);
+                };
+                unsigned char* const ring = sm.ring + warp * (NSLOT * SLOT_BYTES);
+                // rows of a unit that exist and reach the chunk (lane u < 8 <-> row u); the same on both sides
+                auto unit_rows = [&](const It& it, int& i0, int& col0) -> unsigned {
+                    i0 = (b_first + it.k * team) * RBLK;
+                    col0 = 4 * (q_beg + 32 * it.c);
+                    const int i = i0 + lane;
+                    return __ballot_sync(0xffffffffu, lane < RBLK && i > j && i < n && col0 <= i);
+                };
+                auto issue = [&](const It& it) {
+                    int i0, col0;
+                    const unsigned rows = unit_rows(it, i0, col0);
+                    if (rows == 0u) return;
+                    const int slot = (it.u - u_lo) & (NSLOT - 1);
+                    if (lane == 0) {
+                        unsigned long long* bar = &sm.mbar[warp][slot];
+                        mbar_expect_tx(bar, SLOT_BYTES);            // a tiled box always delivers all its bytes (zeros outside the tensor)
+                        tma_box_g2s(ring + slot * SLOT_BYTES, jb.tmap, col0, i0, bar);
+                    }
+                };
+                It pi, ci;
+                pi.u = u_lo; seek(pi, c_first);
+                while (pi.k >= pi.k_end && pi.u < u_hi) seek(pi, pi.c + 1);
+                ci = pi;
+#pragma unroll
+                for (int s_ = 0; s_ < NSLOT; ++s_)
+                    if (pi.u < u_hi) { issue(pi); advance(pi); }
+                int cur_c = -1, q = 0;
+                float4 vv = make_float4(0.f, 0.f, 0.f, 0.f), zc = vv;
+                while (ci.u < u_hi) {
+                    if (ci.c != cur_c) {
+                        if (cur_c >= 0 && q < (ldt >> 2)) {
+                            SMEM_ADD(&smz[4 * q], zc.x); SMEM_ADD(&smz[4 * q + 1], zc.y);
+                            SMEM_ADD(&smz[4 * q + 2], zc.z); SMEM_ADD(&smz[4 * q + 3], zc.w);
+                        }
+                        cur_c = ci.c;
+                        q = q_beg + 32 * cur_c + lane;
+                        vv = *reinterpret_cast<const float4*>(&smv[4 * (q < (ldt >> 2) ? q : q_beg)]);
+                        zc = make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+                    int i0, col0;
+                    const unsigned rows = unit_rows(ci, i0, col0);
+                    const int slot = (ci.u - u_lo) & (NSLOT - 1);
+                    const int k = ci.k;
+                    if (rows != 0u) {
+                        const long long tw0 = prof_on ? clock64() : 0;
+                        mbar_wait_parity(&sm.mbar[warp][slot], (ring_par >> slot) & 1u);
+                        ring_par ^= 1u << slot;
+                        if (prof_on) { prof_wait += clock64() - tw0; ++prof_units; }
+                    }
+                    const unsigned char* sl = ring + slot * SLOT_BYTES + lane * 16;
+                    float acc[RBLK];
+                    // The product is instruction-issue bound (4 warps per scheduler), so the common case -- all 8 rows
+                    // live and the whole 128-column chunk strictly below the diagonal -- runs without a single
+                    // predicate: 10 LDS.128 + 64 FFMA per lane.  Warp-uniform test.
+                    if (i0 > j && i0 + RBLK <= n && col0 + 128 <= i0) {
+                        const float4 va = *reinterpret_cast<const float4*>(&smv[i0]);
+                        const float4 vb = *reinterpret_cast<const float4*>(&smv[i0 + 4]);
+                        const float vi8[RBLK] = {va.x, va.y, va.z, va.w, vb.x, vb.y, vb.z, vb.w};
+#pragma unroll
+                        for (int uu = 0; uu < RBLK; ++uu) {
+                            const float4 t = *reinterpret_cast<const float4*>(sl + uu * 512);
+                            acc[uu] = fmaf(t.x, vv.x, fmaf(t.y, vv.y, fmaf(t.z, vv.z, t.w * vv.w)));
+                            zc.x = fmaf(t.x, vi8[uu], zc.x); zc.y = fmaf(t.y, vi8[uu], zc.y);
+                            zc.z = fmaf(t.z, vi8[uu], zc.z); zc.w = fmaf(t.w, vi8[uu], zc.w);
+                        }
+                    } else {
                         float4 m[RBLK];
 #pragma unroll
                         for (int uu = 0; uu < RBLK; ++uu) {
                             const int i = i0 + uu;
-                            m[uu] = (i > j && i < n && 4 * q <= i)
-                                        ? __ldcg(reinterpret_cast<const float4*>(jb.T + (size_t)i * ldt) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+                            m[uu] = (((rows >> uu) & 1u) && 4 * q <= i) ? *reinterpret_cast<const float4*>(sl + uu * 512)
+                                                                         : make_float4(0.f, 0.f, 0.f, 0.f);
                         }
-                        float acc[RBLK];
                         const bool edge = 4 * q + 3 >= i0;            // this quad touches the diagonal of some row of the block
 #pragma unroll
                         for (int uu = 0; uu < RBLK; ++uu) {
                             float4 t = m[uu];
                             const int i = i0 + uu;
-                            const float vi = (i > j && i < n) ? sm.v[i] : 0.f;
+                            const float vi = (i > j && i < n) ? smv[i] : 0.f;
                             if (edge) {                               // c <= i for the row sum, c < i for the transposed half
                                 const int cc = 4 * q;
                                 if (cc > i) t.x = 0.f;
@@ -488,31 +610,49 @@ __device__ void run_job(const Job& jb, int rank, Smem& sm) {
                             zc.x = fmaf(t.x, vi, zc.x); zc.y = fmaf(t.y, vi, zc.y);
                             zc.z = fmaf(t.z, vi, zc.z); zc.w = fmaf(t.w, vi, zc.w);
                         }
-#pragma unroll
-                        for (int o = 16; o > 0; o >>= 1)
-#pragma unroll
-                            for (int uu = 0; uu < RBLK; ++uu) acc[uu] += __shfl_xor_sync(0xffffffffu, acc[uu], o);
-                        float mine = acc[0];
-#pragma unroll
-                        for (int uu = 1; uu < RBLK; ++uu) if (lane == uu) mine = acc[uu];
-                        if (lane < RBLK) atomicAdd(&sm.ysum[k * RBLK + lane], mine);
                     }
-                    if (q < (ldt >> 2)) {
-                        atomicAdd(&sm.z[4 * q], zc.x); atomicAdd(&sm.z[4 * q + 1], zc.y);
-                        atomicAdd(&sm.z[4 * q + 2], zc.z); atomicAdd(&sm.z[4 * q + 3], zc.w);
-                    }
-                    u = u_end;
-                    ++c;
+                    // 8 row sums over 32 lanes with 9 shuffles: every exchange halves the rows a lane carries
+                    const float tot = row_reduce8(acc);               // lanes with (lane & 3) == 0 hold row lane >> 2
+                    if ((lane & 3) == 0) SMEM_ADD(&smy[k * RBLK + (lane >> 2)], tot);
+                    // every lane's reads of the slot have been consumed by the reductions above: refill it
+                    if (pi.u < u_hi) { issue(pi); advance(pi); }
+                    advance(ci);
+                }
+                if (cur_c >= 0 && q < (ldt >> 2)) {
+                    SMEM_ADD(&smz[4 * q], zc.x); SMEM_ADD(&smz[4 * q + 1], zc.y);
+                    SMEM_ADD(&smz[4 * q + 2], zc.z); SMEM_ADD(&smz[4 * q + 3], zc.w);
                 }
             }
             TRD_TICK(4);
             __syncthreads();                                       // row sums and z complete
+            // team sums of the raw panel inner products written before the |x|^2 barrier (quantities k < jp and 32 + k):
+            // only the NEXT column needs them, so their round trip hides behind the stores below.  One warp per
+            // quantity, all loads of a warp issued before its first reduction, fixed order (same bits on every CTA).
+            constexpr int PER = 64 / NWARP;
+            float qa[PER];
+#pragma unroll
+            for (int u = 0; u < PER; ++u) {
+                const int k = warp + NWARP * u;
+                qa[u] = 0.f;
+                if ((k & 31) < jp) {
+#pragma unroll
+                    for (int it = 0; it < TS / 32; ++it) {
+                        const int r = lane + 32 * it;
+                        if (r < team) qa[u] += __ldcg(jb.part + k * TS + r);
+                    }
+                }
+            }
+            float wj1 = 0.f, vj1 = 0.f;                             // row j+1 of the panels: its v is exactly 1
+            if (warp == 1) {
+                wj1 = lane < jp ? __ldcg(jb.Wp + (size_t)(j + 1) * NB + lane) : 0.f;
+                vj1 = lane < jp ? __ldcg(jb.Vp + (size_t)(j + 1) * NB + lane) : 0.f;
+            }
             // per owned row: publish the own part of y and the reflector (lane u < 8 takes row u of the block)
             float acc_vy = 0.f;
             for (int k = warp; k < K; k += NWARP) {
                 const int i = (b_first + k * team) * RBLK + lane;
                 if (lane < RBLK && i > j && i < n) {
-                    const float vi = sm.v[i], yl = sm.ysum[k * RBLK + lane];
+                    const float vi = smv[i], yl = smy[k * RBLK + lane];
                     jb.y[i] = yl;                                      // own (lower-triangle) part of y_i
                     acc_vy = fmaf(vi, yl, acc_vy);
                     jb.Vp[(size_t)i * NB + jp] = vi;
@@ -521,17 +661,27 @@ __device__ void run_job(const Job& jb, int rank, Smem& sm) {
             }
             // hand z to the team (coalesced) and fold its share of v.y:  v.y = sum_i v_i ylow_i + sum_c v_c z_c
             for (int c = c_al + tid; c < ldt; c += THREADS) {
-                const float zc = sm.z[c];
+                const float zc = smz[c];
                 jb.zpart[(size_t)rank * ldt + c] = zc;
-                acc_vy = fmaf(sm.v[c], zc, acc_vy);
+                acc_vy = fmaf(smv[c], zc, acc_vy);
             }
             acc_vy = warp_sum(acc_vy);
             if (lane == 0) sm.red[2][warp][0] = acc_vy;
+#pragma unroll
+            for (int u = 0; u < PER; ++u) {
+                const float t = warp_sum(qa[u]);
+                if (lane == 0) sm.qraw[warp + NWARP * u] = t;
+            }
             __syncthreads();
             if (tid == 0) {
                 float vy = 0.f;
                 for (int w = 0; w < NWARP; ++w) vy += sm.red[2][w][0];
                 jb.part[64 * TS + rank] = vy;
+            }
+            if (warp == 1) {                                        // s = scale (W^T x) + W[j+1], t = scale (V^T x) + V[j+1]
+                const float scale = sm.scale;
+                sm.q[lane] = lane < jp ? fmaf(scale, sm.qraw[lane], wj1) : 0.f;
+                sm.q[32 + lane] = lane < jp ? fmaf(scale, sm.qraw[32 + lane], vj1) : 0.f;
             }
         }
         TRD_TICK(5);
@@ -580,6 +730,7 @@ __device__ void run_job(const Job& jb, int rank, Smem& sm) {
     if (prof_on) {
         for (int q = 0; q < 9; ++q) jb.prof[q] = prof_acc[q];
         unsigned long long g; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(g)); jb.prof[10] = (long long)g;
+        jb.prof[11] = prof_wait; jb.prof[12] = prof_units;
     }
 #undef TRD_TICK
     __syncthreads();
@@ -587,14 +738,22 @@ __device__ void run_job(const Job& jb, int rank, Smem& sm) {
 
 __global__ void __launch_bounds__(THREADS, 1)
 trd_kernel(const Job* jobs, const int* cta_begin, const int* entries) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
+    float* dynf = reinterpret_cast<float*>(smem_raw + sizeof(Smem));
     __shared__ Job jb;
+    if (threadIdx.x == 0) {
+        for (int w = 0; w < NWARP; ++w)
+            for (int s_ = 0; s_ < NSLOT; ++s_)
+                asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_addr(&sm.mbar[w][s_])));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    uint32_t ring_par = 0;                                       // per warp: phase parity of its ring slots (persists across jobs)
     for (int e = cta_begin[blockIdx.x]; e < cta_begin[blockIdx.x + 1]; ++e) {
         __syncthreads();
         if (threadIdx.x == 0) jb = jobs[entries[2 * e]];
         __syncthreads();
-        run_job(jb, entries[2 * e + 1], sm);
+        run_job(jb, entries[2 * e + 1], sm, dynf, ring_par);
     }
 }
 
@@ -649,6 +808,40 @@ static double job_time(int n, int team) {
     return n * f + 0.0201e-6 * n2 / team + 1.37e-11 * n3 / tp + 0.89e-11 * n3 / team;
 }
 
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+int encode_tmap(void* slot128, const float* T, int n, int ldt) {
+    static EncodeTiledFn encode = nullptr;
+    if (!encode) {
+        cudaDriverEntryPointQueryResult qres;
+        void* fn = nullptr;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn) return -1;
+        encode = (EncodeTiledFn)fn;
+    }
+    static_assert(sizeof(CUtensorMap) == 128, "tensor map slot");
+    alignas(64) CUtensorMap tm;
+    const cuuint64_t dims[2] = {(cuuint64_t)ldt, (cuuint64_t)n};
+    const cuuint64_t strides[1] = {(cuuint64_t)ldt * sizeof(float)};
+    const cuuint32_t box[2] = {128, (cuuint32_t)RBLK};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult cr = encode(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(T), dims, strides, box, estr,
+                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (cr != CUDA_SUCCESS) return (int)cr;
+    memcpy(slot128, &tm, 128);
+    return 0;
+}
+
+// dynamic shared memory of a CTA working on an n x n job in a team of `team`: fixed part + v | z | ysum
+size_t smem_bytes(int n, int team) {
+    const int ldt = (n + 7) & ~7;
+    const int blocks = (n + RBLK - 1) / RBLK;
+    const int ycap = RBLK * ((blocks + team - 1) / team + 1);
+    return sizeof(Smem) + sizeof(float) * (size_t)(2 * ldt + ycap);
+}
+static bool fits(int n, int team) { return smem_bytes(n, team) <= (size_t)SMEM_LIMIT; }
+
 int plan_teams(const int* n, int njobs, int sms, int* team, int* cta_begin, int* entries) {
     static int forced = -2;                                           // KFACB_TRD_TEAM=k: every job on a team of k (tuning aid)
     if (forced == -2) { const char* e = getenv("KFACB_TRD_TEAM"); forced = (e && *e) ? atoi(e) : -1; }
@@ -671,9 +864,9 @@ int plan_teams(const int* n, int njobs, int sms, int* team, int* cta_begin, int*
         for (int a = 0; a < njobs; ++a) {
             const int jn = n[order[a]];
             int tsel = -1;
-            if (forced > 0) tsel = forced > sms ? sms : forced;
-            else for (int t = 1; t <= sms; ++t)                      // smallest team that meets the limit
-                if (job_time(jn, t) <= limit) { tsel = t; break; }
+            if (forced > 0) { tsel = forced > sms ? sms : forced; while (tsel < sms && !fits(jn, tsel)) ++tsel; }
+            else for (int t = 1; t <= sms; ++t)                      // smallest team that meets the limit (and holds its vectors)
+                if (fits(jn, t) && job_time(jn, t) <= limit) { tsel = t; break; }
             if (tsel < 0) return false;
             const double jt = job_time(jn, tsel);
             int k = -1;
@@ -719,12 +912,13 @@ int plan_teams(const int* n, int njobs, int sms, int* team, int* cta_begin, int*
     return used > 0 ? used : 0;        // CTAs in use (the grid); entries written: sum over CTAs
 }
 
-cudaError_t launch(const Job* d_jobs, const int* d_cta_begin, const int* d_entries, int grid, cudaStream_t st) {
+cudaError_t launch(const Job* d_jobs, const int* d_cta_begin, const int* d_entries, int grid, size_t smem, cudaStream_t st) {
     if (grid <= 0) return cudaSuccess;
-    cudaError_t e = cudaFuncSetAttribute(trd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem));
+    if (smem > (size_t)SMEM_LIMIT) return cudaErrorInvalidValue;
+    cudaError_t e = cudaFuncSetAttribute(trd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
     if (e != cudaSuccess) return e;
     void* args[] = {(void*)&d_jobs, (void*)&d_cta_begin, (void*)&d_entries};
-    e = cudaLaunchCooperativeKernel((const void*)trd_kernel, dim3(grid), dim3(THREADS), args, sizeof(Smem), st);
+    e = cudaLaunchCooperativeKernel((const void*)trd_kernel, dim3(grid), dim3(THREADS), args, smem, st);
     count_launch();
     return e;
 }

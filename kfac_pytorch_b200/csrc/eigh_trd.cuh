@@ -10,7 +10,7 @@ namespace trd {
 constexpr int NB = 32;            // panel width = warp size: lane k owns panel column k
 constexpr int THREADS = 512;       // 128 registers per thread: 8 x 16-byte loads in flight per lane in the product
 constexpr int NWARP = THREADS / 32;
-constexpr int MAXN = 8192;        // the reflector vector of one column lives in shared memory
+constexpr int MAXN = 8192;        // the reflector and the transposed-product vectors of a column live in shared memory
 constexpr int NPART = 66;         // partial sums per team member: [0,32) W^T v, [32,64) V^T v, [64] v.y, [65] |x|^2
 constexpr int TS = 160;           // slots per quantity (>= largest team): part[k * TS + rank]
 
@@ -29,6 +29,7 @@ struct Job {
     float* zpart;         // team x ldt: every CTA's transposed contributions z (symmetric product from the lower triangle)
     unsigned* bar;        // team barrier counter (zero on entry)
     long long* prof;      // NULL, or 9 clock64 totals of the phases (debug: KFACB_TRD_PROF=1)
+    const void* tmap;     // CUtensorMap of T (device copy, 128-byte slot): 2-D tiled, box = 128 columns x 8 rows, no swizzle
     int n, ldt, team;
 };
 
@@ -42,7 +43,11 @@ struct Sched {            // host-built: CTA c runs entries [begin[c], begin[c+1
 int plan_teams(const int* n, int njobs, int sms, int* team, int* cta_begin, int* entries);
 
 // launches the persistent kernel (cooperative launch: all CTAs co-resident)
-cudaError_t launch(const Job* d_jobs, const int* d_cta_begin, const int* d_entries, int grid, cudaStream_t st);
+size_t smem_bytes(int n, int team);     // dynamic shared memory a CTA needs for an n x n job in a team of `team`
+cudaError_t launch(const Job* d_jobs, const int* d_cta_begin, const int* d_entries, int grid, size_t smem, cudaStream_t st);
+
+// encodes the tensor map of an n x ldt work array at device address T into a 128-byte host slot (the caller uploads it)
+int encode_tmap(void* slot128, const float* T, int n, int ldt);
 
 // symmetrised copy (lower triangle mirrored) of the inputs into the work arrays; src[j] n x n, dst = jobs[j].T
 cudaError_t launch_copy(const Job* d_jobs, const float* const* d_src, int njobs, int nmax, cudaStream_t st);

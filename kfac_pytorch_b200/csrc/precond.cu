@@ -126,6 +126,55 @@ fin_write_kernel(const FinJob* jobs, int njobs, const float* __restrict__ nu_ptr
     }
 }
 
+// dst[0 .. dG*dW) <- wgrad, dst[dG*dW .. dG*dA) <- bgrad   (FinJob.v doubles as the destination)
+__global__ void __launch_bounds__(256)
+pack_grads_kernel(const FinJob* jobs, int njobs) {
+    const int ji = fin_find_job(jobs, njobs, blockIdx.x);
+    const FinJob jb = jobs[ji];
+    const long tot = (long)jb.dG * jb.dA, nw = (long)jb.dG * jb.dW;
+    const long beg = (long)(blockIdx.x - jb.chunk_begin) * FIN_CHUNK;
+    const long end = min(tot, beg + FIN_CHUNK);
+    float* dst = const_cast<float*>(jb.v);
+    for (long e = beg + threadIdx.x; e < end; e += 256) dst[e] = e < nw ? jb.w[e] : jb.b[e - nw];
+}
+
+// out[0] = sum of the chunk partials (fixed order)
+__global__ void fin_sum_kernel(const double* __restrict__ partial, int nchunks, double* __restrict__ out) {
+    __shared__ double red[32];
+    double s = 0.0;
+    for (int i = threadIdx.x; i < nchunks; i += blockDim.x) s += partial[i];
+    s = warp_sum(s);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += red[i];
+        *out = t;
+    }
+}
+
+// uploads the job table of a finalize-family call; returns the number of chunks (or -1 with the error set)
+static int fin_upload_jobs(const kfacb_layer_t* layers, int count, const float* const* precon, float* const* wgrad,
+                           float* const* bgrad, void* workspace, cudaStream_t st) {
+    FinJob* hj = new FinJob[count > 0 ? count : 1];
+    int chunk = 0;
+    for (int i = 0; i < count; ++i) {
+        const kfacb_layer_t& l = layers[i];
+        const int nA = kfacb_layer_dA(&l), nG = kfacb_layer_dG(&l);
+        if (!precon[i] || !wgrad[i] || (l.has_bias && !bgrad[i])) {
+            delete[] hj;
+            set_error("layer %d: null pointer", i);
+            return -1;
+        }
+        hj[i] = FinJob{precon[i], wgrad[i], bgrad[i], nG, nA, nA - (l.has_bias ? 1 : 0), chunk};
+        chunk += cdiv((long)nA * nG, FIN_CHUNK);
+    }
+    const cudaError_t e = cudaMemcpyAsync(workspace, hj, sizeof(FinJob) * count, cudaMemcpyHostToDevice, st);
+    delete[] hj;
+    if (e != cudaSuccess) { set_error("job table upload failed: %s", cudaGetErrorString(e)); return -1; }
+    return chunk;
+}
+
 }  // namespace kfacb
 
 using namespace kfacb;
@@ -325,6 +374,70 @@ extern "C" int kfacb_finalize_grads(const kfacb_layer_t* layers, int32_t count,
     fin_nu_kernel<<<1, 1024, 0, st>>>(partial, chunk, lr, kl_clip, force_nu_one, nu_out);
     KFACB_CHECK_LAUNCH();
     fin_write_kernel<<<chunk, 256, 0, st>>>(dj, count, nu_out);
+    KFACB_CHECK_LAUNCH();
+    return KFACB_OK;
+}
+
+// ---------------------------------------------------------------------------
+// split finalize + gradient packing for the fused gradient-reduce path (replaces the caller's
+// all-reduce, examples/pytorch_imagenet_resnet.py:371-383, with reduce-to-owner -> precondition -> exchange)
+// ---------------------------------------------------------------------------
+extern "C" int kfacb_pack_grads(const kfacb_layer_t* layers, int32_t count,
+                                const float* const* wgrad, const float* const* bgrad, float* const* dst,
+                                void* workspace, size_t workspace_bytes, kfacb_stream_t stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    KFACB_REQUIRE(layers && wgrad && bgrad && dst && count >= 0, "null argument");
+    if (workspace_bytes < kfacb_finalize_workspace_bytes(layers, count) || ((uintptr_t)workspace & 255)) {
+        set_error("pack workspace too small or misaligned");
+        return KFACB_ERR_WORKSPACE;
+    }
+    if (count == 0) return KFACB_OK;
+    const int chunk = fin_upload_jobs(layers, count, const_cast<const float* const*>(dst), const_cast<float* const*>(wgrad),
+                                      const_cast<float* const*>(bgrad), workspace, st);
+    if (chunk < 0) return KFACB_ERR_ARG;
+    pack_grads_kernel<<<chunk, 256, 0, st>>>((const FinJob*)workspace, count);
+    KFACB_CHECK_LAUNCH();
+    return KFACB_OK;
+}
+
+extern "C" int kfacb_finalize_dot(const kfacb_layer_t* layers, int32_t count,
+                                  const float* const* precon, const float* const* wgrad, const float* const* bgrad,
+                                  double* vg_sum_out, void* workspace, size_t workspace_bytes, kfacb_stream_t stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    KFACB_REQUIRE(layers && precon && wgrad && bgrad && vg_sum_out && count >= 0, "null argument");
+    if (workspace_bytes < kfacb_finalize_workspace_bytes(layers, count) || ((uintptr_t)workspace & 255)) {
+        set_error("finalize workspace too small or misaligned");
+        return KFACB_ERR_WORKSPACE;
+    }
+    if (count == 0) { KFACB_CHECK_CUDA(cudaMemsetAsync(vg_sum_out, 0, sizeof(double), st)); return KFACB_OK; }
+    const int chunk = fin_upload_jobs(layers, count, precon, const_cast<float* const*>(wgrad), const_cast<float* const*>(bgrad),
+                                      workspace, st);
+    if (chunk < 0) return KFACB_ERR_ARG;
+    double* partial = (double*)((char*)workspace + align_up(sizeof(FinJob) * (size_t)(count + 1), 256));
+    fin_dot_kernel<<<chunk, 256, 0, st>>>((const FinJob*)workspace, count, partial);
+    KFACB_CHECK_LAUNCH();
+    fin_sum_kernel<<<1, 1024, 0, st>>>(partial, chunk, vg_sum_out);
+    KFACB_CHECK_LAUNCH();
+    return KFACB_OK;
+}
+
+extern "C" int kfacb_finalize_write(const kfacb_layer_t* layers, int32_t count,
+                                    const float* const* precon, float* const* wgrad, float* const* bgrad,
+                                    const double* vg_sum, float lr, float kl_clip, int32_t force_nu_one, float* nu_out,
+                                    void* workspace, size_t workspace_bytes, kfacb_stream_t stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    KFACB_REQUIRE(layers && precon && wgrad && bgrad && nu_out && count >= 0, "null argument");
+    KFACB_REQUIRE(vg_sum || !(kl_clip > 0.f) || force_nu_one, "vg_sum is required when the KL clip is active");
+    if (workspace_bytes < kfacb_finalize_workspace_bytes(layers, count) || ((uintptr_t)workspace & 255)) {
+        set_error("finalize workspace too small or misaligned");
+        return KFACB_ERR_WORKSPACE;
+    }
+    if (count == 0) return KFACB_OK;
+    const int chunk = fin_upload_jobs(layers, count, precon, wgrad, bgrad, workspace, st);
+    if (chunk < 0) return KFACB_ERR_ARG;
+    fin_nu_kernel<<<1, 32, 0, st>>>(vg_sum, vg_sum ? 1 : 0, lr, kl_clip, force_nu_one || !vg_sum, nu_out);
+    KFACB_CHECK_LAUNCH();
+    fin_write_kernel<<<chunk, 256, 0, st>>>((const FinJob*)workspace, count, nu_out);
     KFACB_CHECK_LAUNCH();
     return KFACB_OK;
 }

@@ -41,6 +41,7 @@ EXPORTS = [
     'kfacb_spd_inverse_workspace_bytes', 'kfacb_pi_damped_inverse',
     'kfacb_precond_workspace_bytes', 'kfacb_precond_eigen', 'kfacb_precond_inverse',
     'kfacb_finalize_workspace_bytes', 'kfacb_finalize_grads',
+    'kfacb_pack_grads', 'kfacb_finalize_dot', 'kfacb_finalize_write',
     'kfacb_precond_eigen_bcast', 'kfacb_precond_inverse_bcast',
     'kfacb_exchange_create', 'kfacb_exchange_handle', 'kfacb_exchange_connect', 'kfacb_exchange_slab',
     'kfacb_exchange_peer_deltas', 'kfacb_exchange_begin', 'kfacb_exchange_signal', 'kfacb_exchange_push',
@@ -103,6 +104,10 @@ def load_library(path: Optional[str] = None):
     lib.kfacb_finalize_workspace_bytes.restype = C.c_size_t
     lib.kfacb_finalize_grads.argtypes = [LP, C.c_int32, PP, PP, PP, C.c_float, C.c_float,
                                          C.c_int32, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
+    lib.kfacb_pack_grads.argtypes = [LP, C.c_int32, PP, PP, PP, C.c_void_p, C.c_size_t, C.c_void_p]
+    lib.kfacb_finalize_dot.argtypes = [LP, C.c_int32, PP, PP, PP, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
+    lib.kfacb_finalize_write.argtypes = [LP, C.c_int32, PP, PP, PP, C.c_void_p, C.c_float, C.c_float, C.c_int32,
+                                         C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
     I64P = C.POINTER(C.c_int64)
     lib.kfacb_precond_eigen_bcast.argtypes = [LP, C.c_int32, PP, PP, PP, PP, PP, PP, PP, C.c_float, C.c_int32, I64P,
                                               C.c_void_p, C.c_size_t, C.c_void_p]
@@ -298,6 +303,40 @@ class NativeEngine:
         with torch.cuda.device(self.device):
             self._call(self.lib.kfacb_finalize_grads(
                 d, n, _ptrs(precon), _ptrs(wgrad), _ptrs(bgrad), lr,
+                float(kl_clip) if kl_clip else 0.0, int(force_nu_one), nu_out.data_ptr(),
+                ws.data_ptr(), ws.numel(), self._stream()))
+
+
+    # -- (4b) fused gradient-reduce path: pack / owner-partial dot / rewrite from the global sum ------------------
+    def _fin_ws(self, d, n):
+        return self._workspace('finalize', self.lib.kfacb_finalize_workspace_bytes(d, n))
+
+    def pack_grads(self, layers, wgrad, bgrad, dst):
+        for t in list(wgrad) + list(bgrad) + list(dst):
+            if t is not None:
+                _check_f32(t, 'pack operand')
+        d, n = _descs(layers), len(layers)
+        ws = self._fin_ws(d, n)
+        with torch.cuda.device(self.device):
+            self._call(self.lib.kfacb_pack_grads(d, n, _ptrs(wgrad), _ptrs(bgrad), _ptrs(dst),
+                                                 ws.data_ptr(), ws.numel(), self._stream()))
+
+    def finalize_dot(self, layers, precon, wgrad, bgrad, vg_sum_out: torch.Tensor):
+        if vg_sum_out.dtype != torch.float64 or vg_sum_out.numel() < 1:
+            raise KfacbError('finalize_dot: vg_sum_out must be a float64 device tensor')
+        d, n = _descs(layers), len(layers)
+        ws = self._fin_ws(d, n)
+        with torch.cuda.device(self.device):
+            self._call(self.lib.kfacb_finalize_dot(d, n, _ptrs(precon), _ptrs(wgrad), _ptrs(bgrad),
+                                                   vg_sum_out.data_ptr(), ws.data_ptr(), ws.numel(), self._stream()))
+
+    def finalize_write(self, layers, precon, wgrad, bgrad, vg_sum: Optional[torch.Tensor], lr: float,
+                       kl_clip: Optional[float], force_nu_one: bool, nu_out: torch.Tensor):
+        d, n = _descs(layers), len(layers)
+        ws = self._fin_ws(d, n)
+        with torch.cuda.device(self.device):
+            self._call(self.lib.kfacb_finalize_write(
+                d, n, _ptrs(precon), _ptrs(wgrad), _ptrs(bgrad), None if vg_sum is None else vg_sum.data_ptr(), lr,
                 float(kl_clip) if kl_clip else 0.0, int(force_nu_one), nu_out.data_ptr(),
                 ws.data_ptr(), ws.numel(), self._stream()))
 

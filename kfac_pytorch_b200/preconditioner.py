@@ -119,7 +119,7 @@ class KFAC(optim.Optimizer):
                  kl_clip=0.001, factor_decay=0.95, exclude_vocabulary_size=None,
                  hook_enabled=True, exclude_parts='', *, partition='round_robin', engine=None,
                  communicate_inverse_or_not=False, distribute_layer_factors=None,
-                 overlap_factor_capture=False):
+                 overlap_factor_capture=False, fuse_grad_reduce=False):
         defaults = dict(lr=lr, damping=damping, fac_update_freq=fac_update_freq,
                         kfac_update_freq=kfac_update_freq)
         super().__init__(model.parameters(), defaults)
@@ -147,6 +147,13 @@ class KFAC(optim.Optimizer):
         # stream, so the SYRKs overlap the rest of the forward / backward pass and the captured activations are
         # released as soon as their kernel has run (keyword-only; DP variants; not part of the reference signature)
         self.overlap_factor_capture = bool(overlap_factor_capture)
+        # the caller does NOT all-reduce the gradients; step() reduces each layer's gradient to its
+        # owner only (averaged), the owner preconditions it, and the existing exchange distributes the result --
+        # half the gradient bytes on the wire of all-reduce + exchange.  The KL-clip sum is formed from the owners'
+        # partials with one 8-byte all-reduce (keyword-only; DP variants; not part of the reference signature)
+        self.fuse_grad_reduce = bool(fuse_grad_reduce)
+        self._gslab = None
+        self._vg = None
         self._cap_stream = None
         self._cap_done = {'a': set(), 'g': set()}
 
@@ -477,6 +484,7 @@ class KFAC(optim.Optimizer):
         else:
             self._slab = torch.zeros(max(off, 1), dtype=torch.float32, device=dev)
         self._slab_segments = seg
+        self._slab_offsets = offs
         for i, m in enumerate(self.modules):
             d = self._static[i]
             self.m_precon_grad[m] = self._slab[offs[i]:offs[i] + d.dA * d.dG].view(d.dG, d.dA)
@@ -506,6 +514,61 @@ class KFAC(optim.Optimizer):
             w.append(wg); b.append(bg)
         return w, b
 
+    # ------------------------------------------------ fused gradient reduce (8f rank 2)
+    def _fused_reduce_active(self) -> bool:
+        return self.fuse_grad_reduce and self.is_dp and backend.comm.size() > 1
+
+    def _reduce_grads_to_owners(self):
+        """LOCAL (un-averaged) gradients -> averaged gradient of every layer on its owner only: one pack kernel into a
+        send slab laid out like the exchange slab (owner-contiguous, per layer [W | b]), then one reduce per owner
+        segment.  Replaces the caller's all-reduce (examples/pytorch_imagenet_resnet.py:371-383)."""
+        eng = self._get_engine()
+        self._ensure_slab()
+        if self._gslab is None:
+            self._gslab = torch.empty(self._slab.numel(), dtype=torch.float32, device=self._device())
+        idx = list(range(len(self.modules)))
+        w, b = self._grads(idx)
+        dst = [self._gslab[self._slab_offsets[i]:self._slab_offsets[i] + self._static[i].dA * self._static[i].dG]
+               for i in idx]
+        eng.pack_grads(self._static, w, b, dst)
+        handles = []
+        for r, (beg, end) in enumerate(self._slab_segments):
+            if beg is not None:
+                handles.append(backend.comm.reduce_async_(self._gslab[beg:end], r, backend.comm.Average))
+        for h in handles:
+            backend.comm.synchronize(h)
+
+    def _owner_grads(self, owned):
+        """Views of the reduced send slab as (wgrad, bgrad) of the owned layers."""
+        w, b = [], []
+        for i in owned:
+            st = self._static[i]
+            seg = self._gslab[self._slab_offsets[i]:self._slab_offsets[i] + st.dA * st.dG]
+            nw = st.dG * (st.dA - st.has_bias)
+            w.append(seg[:nw])
+            b.append(seg[nw:] if st.has_bias else None)
+        return w, b
+
+    def _update_grad_fused(self):
+        """KL clip from the owners' partial sums (8-byte all-reduce) + rewrite of every gradient from the exchanged
+        slab (kfac_preconditioner_inv.py:188-217; the rewrite only needs nu and v)."""
+        eng = self._get_engine()
+        owned = self._owned()
+        if self._vg is None:
+            self._vg = torch.zeros(1, dtype=torch.float64, device=self._device())
+        use_clip = self.kl_clip is not None and not self.exclude_communicate_inverse
+        if use_clip:
+            w, b = self._owner_grads(owned)
+            eng.finalize_dot([self._static[i] for i in owned], [self.m_precon_grad[self.modules[i]] for i in owned],
+                             w, b, self._vg)
+            backend.comm.allreduce_(self._vg, op=backend.comm.Sum)
+        idx = list(range(len(self.modules)))
+        w, b = self._grads(idx)
+        eng.finalize_write(self._static, [self.m_precon_grad[m] for m in self.modules], w, b,
+                           self._vg if use_clip else None, float(self.lr), self.kl_clip, not use_clip, self._nu)
+        if self._use_exchange():
+            self._ex.release()
+
     def _compute_pred(self):
         """Owner-only two-sided product (eigen_dp.py:78-93 / inv_dp.py:126-138)."""
         eng = self._get_engine()
@@ -518,7 +581,7 @@ class KFAC(optim.Optimizer):
             self._ex.begin()                   # every peer has finished reading the previous step's slab
         if owned:
             descs = [self._static[i] for i in owned]
-            w, b = self._grads(owned)
+            w, b = self._owner_grads(owned) if self._fused_reduce_active() else self._grads(owned)
             out = [self.m_precon_grad[self.modules[i]] for i in owned]
             mods = [self.modules[i] for i in owned]
             deltas = self._ex.peer_deltas if (use_ex and self._ex_fused) else None
@@ -638,6 +701,9 @@ class KFAC(optim.Optimizer):
                 if backend.comm.size() > 1:
                     self._communicate_inverse()
 
+        if self._fused_reduce_active() and not self.exclude_compute_inverse:
+            self._reduce_grads_to_owners()
+
         if not self.exclude_compute_inverse:
             self._compute_pred()
 
@@ -647,7 +713,10 @@ class KFAC(optim.Optimizer):
                 self._communicate_pred()
 
         if not self.exclude_compute_inverse:
-            self._update_grad_in_place()
+            if self._fused_reduce_active():
+                self._update_grad_fused()
+            else:
+                self._update_grad_in_place()
 
         self.steps += 1
         self.m_a, self.m_g = {}, {}

@@ -43,14 +43,21 @@ class OracleEngine:
             Ad, Gd, a_inv, g_inv = orc.pi_damped_inverses(Ai, Gi, damping)
             Ai.copy_(Ad); Gi.copy_(Gd); iA.copy_(a_inv); iG.copy_(g_inv)
 
+    @staticmethod
+    def _gm(d, w, b):
+        if w.dim() == 1:      # fused gradient-reduce path: flat views [W | b] of the reduced send slab
+            w = w.reshape(d.dG, -1)
+            b = None if b is None else b.reshape(-1)
+        return orc.grad_matrix(spec_of(d), w, b)
+
     def precond_eigen(self, layers, QA, QG, dA, dG, wgrad, bgrad, out, damping, peer_deltas=None):
         for d, qa, qg, da, dg, w, b, o in zip(layers, QA, QG, dA, dG, wgrad, bgrad, out):
-            gm = orc.grad_matrix(spec_of(d), w, b)
+            gm = self._gm(d, w, b)
             o.copy_(orc.precondition_eigen(gm, qa, da, qg, dg, damping))
 
     def precond_inverse(self, layers, invA, invG, wgrad, bgrad, out, peer_deltas=None):
         for d, ia, ig, w, b, o in zip(layers, invA, invG, wgrad, bgrad, out):
-            gm = orc.grad_matrix(spec_of(d), w, b)
+            gm = self._gm(d, w, b)
             o.copy_(orc.precondition_inverse(gm, ia, ig))
 
     def finalize(self, layers, precon, wgrad, bgrad, lr, kl_clip, force_nu_one, nu_out):
@@ -64,6 +71,32 @@ class OracleEngine:
         nu = 1.0 if force_nu_one else orc.kl_clip_scale(vs, gs, lr, kl_clip)
         nu_out.fill_(nu)
         for (vw, vb), w, b in zip(splits, wgrad, bgrad):
+            w.copy_(vw * nu)
+            if b is not None:
+                b.copy_(vb * nu)
+
+    # ---- fused gradient-reduce path (kfacb_pack_grads / kfacb_finalize_dot / kfacb_finalize_write) ----
+    def pack_grads(self, layers, wgrad, bgrad, dst):
+        for d, w, b, o in zip(layers, wgrad, bgrad, dst):
+            nw = w.numel()
+            o[:nw].copy_(w.reshape(-1))
+            if b is not None:
+                o[nw:].copy_(b.reshape(-1))
+
+    def finalize_dot(self, layers, precon, wgrad, bgrad, vg_sum_out):
+        tot = 0.0
+        for d, v, w, b in zip(layers, precon, wgrad, bgrad):
+            g = torch.cat([w.reshape(v.shape[0], -1), b.reshape(-1, 1)], 1) if b is not None else w.reshape(v.shape)
+            tot += float((v.double() * g.double()).sum())
+        vg_sum_out.fill_(tot)
+
+    def finalize_write(self, layers, precon, wgrad, bgrad, vg_sum, lr, kl_clip, force_nu_one, nu_out):
+        nu = 1.0
+        if kl_clip and kl_clip > 0 and not force_nu_one and vg_sum is not None:
+            nu = min(1.0, (kl_clip / abs(float(vg_sum[0]) * lr * lr)) ** 0.5)
+        nu_out.fill_(nu)
+        for d, v, w, b in zip(layers, precon, wgrad, bgrad):
+            vw, vb = orc.split_preconditioned(spec_of(d), v, w.shape, None if b is None else b.shape)
             w.copy_(vw * nu)
             if b is not None:
                 b.copy_(vb * nu)

@@ -245,3 +245,58 @@ def test_eigh_team_scheduler_is_sane_for_resnet50():
     lone = (ctypes.c_int32 * 1)(4608)
     out1 = (ctypes.c_int32 * 1)()
     assert lib.kfacb_eigh_plan_teams(lone, 1, 148, out1) == out1[0] >= 64      # a lone big factor gets most of the GPU
+
+
+def _fused_worker(rank, port, q, variant):
+    import os
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE='2')
+    dist.init_process_group('gloo', rank=rank, world_size=2)
+    try:
+        from kfac_pytorch_b200 import backend
+        import kfac_pytorch_b200 as kfac
+        from tests.oracle_engine import OracleEngine
+        backend.comm = None
+        backend.init('Torch')
+        res = {}
+        for fused in (False, True):
+            torch.manual_seed(5)
+            model = torch.nn.Sequential(torch.nn.Linear(7, 6), torch.nn.Tanh(), torch.nn.Linear(6, 5, bias=False),
+                                        torch.nn.Tanh(), torch.nn.Linear(5, 3))
+            pre = kfac.get_kfac_module(variant)(model, lr=0.1, damping=0.03, kl_clip=0.001, engine=OracleEngine(),
+                                                fuse_grad_reduce=fused)
+            gen = torch.Generator().manual_seed(100 + rank)            # every rank has its own mini-batch
+            for s in range(3):
+                x = torch.randn(9, 7, generator=gen)
+                model.zero_grad()
+                model(x).square().mean().backward()
+                if not fused:                                          # the caller's gradient averaging (Horovod / DDP)
+                    for p in model.parameters():
+                        dist.all_reduce(p.grad)
+                        p.grad.div_(2)
+                pre.step()
+            res[fused] = [p.grad.detach().numpy().copy() for p in model.parameters()]     # numpy: no fd passing
+        q.put((rank, res))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize('variant', ['eigen_dp', 'inverse_dp'])
+def test_fused_gradient_reduce_matches_allreduce_then_step(variant):
+    """SURVEY 8(f) rank 2 on 2 gloo ranks: reduce-to-owner -> precondition -> exchange + KL clip from the owners' partial
+    sums gives the gradients of `all-reduce, then step()` (examples/pytorch_imagenet_resnet.py:371-383 followed by
+    kfac_preconditioner_base.py:185-230) on every rank."""
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = 29700 + (os.getpid() % 200)
+    procs = [ctx.Process(target=_fused_worker, args=(r, port, q, variant)) for r in range(2)]
+    for p in procs:
+        p.start()
+    out = dict(q.get(timeout=120) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+    for r in range(2):
+        for a, b in zip(out[r][False], out[r][True]):
+            assert np.allclose(a, b, rtol=2e-4, atol=1e-7), np.abs(a - b).max()     # fp32: gloo sums in another order
+    for a, b in zip(out[0][True], out[1][True]):
+        assert np.array_equal(a, b)         # every rank ends with identical gradients

@@ -208,3 +208,60 @@ def test_overlapped_factor_capture_refuses_gradient_accumulation():
     with pytest.raises(RuntimeError, match='exactly one forward/backward'):
         model(x).sum().backward()
     assert pre.steps == 0
+
+
+def _fused_cuda_worker(rank, port, q, transport, exchange, variant):
+    sys.path.insert(0, ROOT)
+    import torch.distributed as dist
+    import kfac_pytorch_b200 as kfac
+    from kfac_pytorch_b200 import backend
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port), LOCAL_RANK=str(rank), KFACB_EXCHANGE=exchange)
+    ngpu = torch.cuda.device_count()
+    dev = torch.device('cuda', rank % ngpu)
+    torch.cuda.set_device(dev)
+    dist.init_process_group(transport, rank=rank, world_size=2)
+    backend.comm = None
+    backend.init('Torch')
+    res = {}
+    for fused in (False, True):
+        model = _conv_net(dev)
+        pre = kfac.get_kfac_module(variant)(model, lr=0.1, damping=0.03, kl_clip=0.001, fuse_grad_reduce=fused)
+        gen = torch.Generator(device=dev).manual_seed(40 + rank)       # every rank has its own mini-batch
+        for s in range(3):
+            x = torch.randn(8, 3, 12, 12, device=dev, generator=gen)
+            y = torch.randint(0, 10, (8,), device=dev, generator=gen)
+            model.zero_grad()
+            torch.nn.functional.cross_entropy(model(x), y).backward()
+            if not fused:                                              # the caller's gradient averaging
+                for p in model.parameters():
+                    dist.all_reduce(p.grad)
+                    p.grad.div_(2)
+            pre.step()
+        torch.cuda.synchronize()
+        res[fused] = [p.grad.detach().cpu().numpy().copy() for p in model.parameters()]
+    q.put((rank, res))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize('variant', ['eigen_dp', 'inverse_dp'])
+def test_fused_gradient_reduce_on_device(variant):
+    """SURVEY 8(f) rank 2 through the CUDA engine (kfacb_pack_grads / kfacb_finalize_dot / kfacb_finalize_write): two ranks,
+    reduce-to-owner -> precondition -> exchange equals all-reduce followed by step(); NCCL + peer-memory exchange on
+    two GPUs, gloo + slab broadcast when the box has one."""
+    two = torch.cuda.device_count() >= 2
+    transport, exchange = ('nccl', 'p2p') if two else ('gloo', 'nccl')
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = 29800 + (os.getpid() % 100)
+    procs = [ctx.Process(target=_fused_cuda_worker, args=(r, port, q, transport, exchange, variant)) for r in range(2)]
+    for p in procs:
+        p.start()
+    out = dict(q.get(timeout=600) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+    for r in range(2):
+        for a, b in zip(out[r][False], out[r][True]):
+            assert rel_err(a, b) < 1e-4, rel_err(a, b)
+    for a, b in zip(out[0][True], out[1][True]):
+        np.testing.assert_array_equal(a, b)

@@ -1,6 +1,9 @@
 mkdir -p gpurun_out
-T=r2h
+T=${1:-r2o}
 rm -f gpurun_out/${T}_*
-R50="147 $(yes 256 | head -26 | tr '\n' ' ') $(yes 512 | head -19 | tr '\n' ' ') 576 576 576 1000 $(yes 1024 | head -14 | tr '\n' ' ') 1152 1152 1152 1152 2048 2048 2048 2048 2048 2048 2049 2304 2304 2304 2304 2304 2304 4608 4608 4608"
-( KFACB_TRD_PROF=1 timeout 300 python tools/eigh_probe.py $R50 2>&1 | grep -v "eig_err" ) > gpurun_out/${T}_r50_prof.log 2>&1
+( timeout 600 python -m pytest tests/test_kernels_gpu.py -m gpu -q --timeout 900 -x -k eigh 2>&1 | tail -3 ) > gpurun_out/${T}_tests.log 2>&1
+( KFACB_TRD_PROF=1 KFACB_TRD_TEAM=32 timeout 200 python tools/eigh_probe.py 4608 2>&1 | tail -3 ) >> gpurun_out/${T}_probe.log 2>&1
+( timeout 200 python tools/eigh_probe.py 4608 2>&1 | tail -2 ) >> gpurun_out/${T}_probe.log 2>&1
+( timeout 200 python tools/eigh_probe.py 129 147 513 1000 2304 ) >> gpurun_out/${T}_probe.log 2>&1
 ( timeout 900 python bench.py --steps 5 --warmup 3 --no-cpu-baseline 2>gpurun_out/${T}_bench.err | tail -1 ) > gpurun_out/${T}_bench_n1.json
+( timeout 900 python -m pytest tests/test_parity_gpu.py -m gpu -q --timeout 600 -k "overlapped or fused" 2>&1 | tail -8 ) > gpurun_out/${T}_tests2.log 2>&1
