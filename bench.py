@@ -14,17 +14,23 @@ ours (default): the CUDA path through the drop-in Python API / C ABI.
     barrier + synchronize on both sides, max over ranks).
   * `e2e`: the same step driven from pinned HOST buffers: per step H2D of every
     owned a / g and of all gradients, step(), D2H of all rewritten gradients.
-  * `roofline`: the dominant kernel of the step (the Jacobi row-update GEMM, HBM
-    bound) measured live with CUDA events in an extra untimed profiled step;
-    every phase is listed under `phases` with its algorithmic TFLOP/s and GB/s
-    (SURVEY.md section 8d conventions).
-  * `cpu_baseline`: the oracle (CPU restatement of the reference) on this box's
-    host cores on a bounded sample (one layer per distinct shape class, scaled by
-    class multiplicity).
+  * `roofline`: SURVEY.md section 8(d) -- the dominant PHASE (eigendecomposition / inverse of
+    every owned factor) as sum 9 n^3 (n^3 for the inverse) of the max-loaded rank over its
+    CUDA-event time against the dense-TF32 roofline, `traffic` = DRAM bytes of the dominant
+    kernel from the committed ncu capture (profiles/r02_ncu_traffic.json); under
+    `roofline.kernel` the dominant KERNEL (the persistent Householder tridiagonalisation,
+    HBM bound) from CUDA events the library records around its stages in the LAST TIMED step
+    (no profiling mode: the timed plan is the profiled plan).  Every phase is listed under
+    `phases` with its algorithmic TFLOP/s and GB/s.
+  * `eig_check`: after the timed loop, reconstruction and orthogonality of the largest owned
+    factor of every rank (max over ranks): a truncated / skipped decomposition cannot hide.
+  * `cpu_baseline`: one full step of the vendored UNMODIFIED reference (oracle/_ref) on this
+    box's host cores; the class-sampled oracle port only if oracle/_ref is absent.
 
-reference (--impl reference): the reference's own CPU algorithm (oracle port; the
-  reference is pure Python/PyTorch and is not present on the GPU box) on the host
-  cores, same workload / metric / unit; every step is the bounded class sample.
+reference (--impl reference): the UNMODIFIED reference package (oracle/_ref, vendored by the
+  committed recipe oracle/make_ref.py) through its own public API on the host cores, same
+  workload / metric / unit, all layers, a bounded number of full steps; --impl reference_gpu
+  runs the same package on the GPU through torch CUDA (cuSOLVER) as an informational row.
 """
 from __future__ import annotations
 

@@ -795,17 +795,18 @@ __global__ void trd_copy_kernel(const Job* jobs, const float* const* src) {
 // ---------------------------------------------------------------------------
 // Cost model of one job on a team (seconds), fitted to B200 measurements of single matrices on forced team sizes
 // (tools/trd_calib.py, profiles/r02_trd_calibration.txt; n = 256 .. 4608, teams 1 .. 147, all points within 6 %):
-//   per column: the dependent chain of short phases + two team barriers -- 9.7 us on a single CTA, 11.6 us on teams
+//   per column: the dependent chain of short phases + two team barriers -- 7.4 us on a single CTA, 11.8 us on teams
 //               up to 16, + 1.5 us per doubling beyond (barrier fan-in, slowest-member wait);
-//   row phases (finish w, form the column, publish y / the reflector): 20 ns per (row, column) pair / team;
-//   symmetric product: 2/3 n^3 bytes at 48.6 GB/s per SM (16 warps x 4 KB in flight) up to the HBM ceiling (113 SMs);
-//   rank-2k updates: 4/3 n^3 flops at 150 GFLOP/s per SM.
+//   row phases (finish w, form the column, publish y / the reflector): 25 ns per (row, column) pair / team;
+//   symmetric product + rank-2k updates: 1.7e-11 s n^3 per SM while the matrix is L2-resident next to its
+//               neighbours (n <= ~2700), 2.05e-11 above (the product is instruction-issue bound at ~40 - 60 GB/s per
+//               SM, so the HBM ceiling is not reached even by 147 CTAs).
 static double job_time(int n, int team) {
-    double f = team > 1 ? 11.6e-6 : 9.7e-6;
+    double f = team > 1 ? 11.8e-6 : 7.4e-6;
     if (team > 16) f += 1.5e-6 * log2((double)team / 16.0);
     const double n2 = (double)n * n, n3 = n2 * n;
-    const double tp = team < 113 ? team : 113;
-    return n * f + 0.0201e-6 * n2 / team + 1.37e-11 * n3 / tp + 0.89e-11 * n3 / team;
+    const double c2 = n2 * 4.0 < 30e6 ? 1.7e-11 : 2.05e-11;
+    return n * f + (0.0246e-6 * n2 + c2 * n3) / team;
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
