@@ -33,7 +33,7 @@
 namespace kfacb {
 namespace dc {
 
-constexpr int LEAF = 64;
+constexpr int LEAF = 32;
 constexpr int PB = 128;                  // reflectors per block reflector of the back-transformation
 constexpr int YCH = 512;                 // split-K chunk of Y = Zt V^T (bounds the in-TMEM accumulation chain)
 constexpr float FEPS = 5.9604645e-8f;    // 2^-24

@@ -77,19 +77,21 @@ __device__ __forceinline__ void mbar_wait_parity(unsigned long long* bar, uint32
 // generic-proxy writes to global memory (rank-2k update) before later async-proxy (TMA) reads of the same locations
 __device__ __forceinline__ void fence_proxy_async_global() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
 
-__device__ __forceinline__ void team_barrier(unsigned* ctr, unsigned& target, int team) {
-    fence_proxy_async_global();                                  // this thread's global writes vs. later TMA reads (any CTA of the team)
+// Team barrier: one release-arrival + acquire-poll on a counter in L2 by thread 0, bracketed by CTA barriers (the CTA's
+// writes are ordered before the arrival through bar.sync cumulativity; every global load of the kernel is .cg, so
+// no stale L1 line can be read after the acquire).  `tma_fence`: the barriers around the rank-2k update, the only
+// place where generic-proxy writes (the updated trailing matrix) are later read through the async proxy (TMA).
+__device__ __forceinline__ void team_barrier(unsigned* ctr, unsigned& target, int team, bool tma_fence = false) {
+    if (tma_fence) fence_proxy_async_global();
     __syncthreads();
     if (team > 1) {
         target += (unsigned)team;
         if (threadIdx.x == 0) {
-            __threadfence();                                     // the CTA's writes (ordered by the barrier above) before the arrival
-            asm volatile("red.relaxed.gpu.global.add.u32 [%0], 1;" ::"l"(ctr) : "memory");
+            asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(ctr) : "memory");
             unsigned v;
             do {
-                asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
+                asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
             } while (v < target);
-            __threadfence();                                     // acquire side (also drops stale L1 lines)
         }
         __syncthreads();
     }
@@ -171,7 +173,7 @@ __device__ __forceinline__ void prologue_finish(Smem& sm, int kc, bool want_row,
     }
 }
 
-// A[R0.., R0..] -= V W^T + W V^T over the first kc panel columns; tiles of 128x128 dealt to the team.
+// A[R0.., R0..] -= V W^T + W V^T (lower triangle of 128x128 tiles) over the first kc panel columns; tiles dealt to the team.
 // 16 warps = 4 x 4, lanes = 4 (row groups of 8) x 8 (column groups of 4): 8x4 outputs per thread; per k a warp
 // reads 6 shared-memory wavefronts (broadcast within a group) for 64 FMAs -> FMA bound.
 __device__ __noinline__ void rank2k_update(const Job& jb, Smem& sm, int R0, int kc, int rank) {
@@ -184,8 +186,13 @@ __device__ __noinline__ void rank2k_update(const Job& jb, Smem& sm, int R0, int 
     const int col4 = 32 * (warp & 3) + 4 * (lane & 7);
     const bool aligned = (R0 & 3) == 0;
     float (*op)[NB][OP_PITCH] = reinterpret_cast<float (*)[NB][OP_PITCH]>(sm.ring);
-    for (int q = rank; q < nt * nt; q += jb.team) {
-        const int ti = q / nt, tj = q - ti * nt;
+    // only the LOWER triangle of tiles (diagonal tiles in full): nothing reads the trailing matrix above the diagonal
+    // any more (the product reads c <= i, the column of phase A comes from T[i][j]) -- half the update work
+    for (int q = rank; q < nt * (nt + 1) / 2; q += jb.team) {
+        int ti = (int)((sqrtf(8.f * (float)q + 1.f) - 1.f) * 0.5f);
+        while (ti * (ti + 1) / 2 > q) --ti;
+        while ((ti + 1) * (ti + 2) / 2 <= q) ++ti;
+        const int tj = q - ti * (ti + 1) / 2;
         __syncthreads();
 #pragma unroll
         for (int it = 0; it < (128 * 8) / THREADS; ++it) {
@@ -352,7 +359,7 @@ __device__ void run_job(const Job& jb, int rank, Smem& sm, float* dynf, uint32_t
                     const bool ok = i >= j && i < n;
                     vk[u] = (ok && lane < jp) ? __ldcg(jb.Vp + (size_t)i * NB + lane) : 0.f;
                     wk[u] = (ok && lane < jp - 1) ? __ldcg(jb.Wp + (size_t)i * NB + lane) : 0.f;
-                    tji[u] = ok ? __ldcg(jb.T + (size_t)j * ldt + i) : 0.f;
+                    tji[u] = ok ? __ldcg(jb.T + (size_t)i * ldt + j) : 0.f;      // column j from the lower triangle
                 }
                 if (jp > 0) partial_y(jb, blk, yi);                  // per-lane partials; reduced together with the panel dot
             };
@@ -721,7 +728,7 @@ __device__ void run_job(const Job& jb, int rank, Smem& sm, float* dynf, uint32_t
             team_barrier(jb.bar, target, team);
             TRD_TICK(7);
             rank2k_update(jb, sm, j + 1, jp + 1, rank);
-            team_barrier(jb.bar, target, team);
+            team_barrier(jb.bar, target, team, true);
             TRD_TICK(8);
             j0 = j + 1;
         }
@@ -798,15 +805,14 @@ __global__ void trd_copy_kernel(const Job* jobs, const float* const* src) {
 //   per column: the dependent chain of short phases + two team barriers -- 7.4 us on a single CTA, 11.8 us on teams
 //               up to 16, + 1.5 us per doubling beyond (barrier fan-in, slowest-member wait);
 //   row phases (finish w, form the column, publish y / the reflector): 25 ns per (row, column) pair / team;
-//   symmetric product + rank-2k updates: 1.7e-11 s n^3 per SM while the matrix is L2-resident next to its
-//               neighbours (n <= ~2700), 2.05e-11 above (the product is instruction-issue bound at ~40 - 60 GB/s per
-//               SM, so the HBM ceiling is not reached even by 147 CTAs).
+//   symmetric product + rank-2k updates: 2.05e-11 s n^3 per SM (the product is instruction-issue bound at ~40 - 60 GB/s
+//               per SM, so the HBM ceiling is not reached even by 147 CTAs).  A matrix that is L2-resident while it runs
+//               ALONE measures 1.7e-11, but inside a batch nothing stays resident: the in-batch figure is used.
 static double job_time(int n, int team) {
     double f = team > 1 ? 11.8e-6 : 7.4e-6;
     if (team > 16) f += 1.5e-6 * log2((double)team / 16.0);
     const double n2 = (double)n * n, n3 = n2 * n;
-    const double c2 = n2 * 4.0 < 30e6 ? 1.7e-11 : 2.05e-11;
-    return n * f + (0.0246e-6 * n2 + c2 * n3) / team;
+    return n * f + (0.0246e-6 * n2 + 2.05e-11 * n3) / team;
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
