@@ -177,7 +177,7 @@ __global__ void dc_zero_kernel(const DcMat* mats, const DcMerge* merges, int in)
 __global__ void __launch_bounds__(1024)
 dc_prep_kernel(const DcMat* mats, const DcMerge* merges, DcState* states, int in, int nmax) {
     extern __shared__ float smem[];
-    __shared__ float s_red[2][32];
+    __shared__ float s_red[3][32];
     const DcMerge mg = merges[blockIdx.x];
     const DcMat mt = mats[mg.mat];
     const int n1 = mg.n1, n2 = mg.n2, nm = n1 + n2, off = mg.off, tid = threadIdx.x;
@@ -195,7 +195,13 @@ dc_prep_kernel(const DcMat* mats, const DcMerge* merges, DcState* states, int in
     const float es = mt.e[off + n1 - 1];
     const float sgn = es >= 0.f ? 1.f : -1.f, rho = 2.f * fabsf(es);
     const float* Zin = mt.Z[in];
-    float dmax = 0.f, zmax = 0.f;
+    float dmax = 0.f, zmax = 0.f, tmax = 0.f;
+    // max-norm of the whole tridiagonal matrix: LAPACK (sstedc) scales the problem to unit norm before the merges, so
+    // slaed2's tolerance 8 eps max(|d|max, |z|max) compares the dimensionless z with d ~ 1.  Unscaled, z has to carry
+    // the scale of the matrix -- K-FAC's conv A factors are ~0.0025 I + .., and an absolute 8 eps |z|max deflated them
+    // far too eagerly (measured: reconstruction 6e-5 instead of 1e-6 on ResNet-50 conv1 at step 1)
+    for (int i = tid; i < mt.n; i += blockDim.x)
+        tmax = fmaxf(tmax, fmaxf(fabsf(mt.d[i]), i + 1 < mt.n ? fabsf(mt.e[i]) : 0.f));
     for (int i = tid; i < nm; i += blockDim.x) {
         const float dv = din[i];
         const float zv = (i < n1 ? Zin[(size_t)(off + i) * mt.ldz + off + n1 - 1]
@@ -206,8 +212,9 @@ dc_prep_kernel(const DcMat* mats, const DcMerge* merges, DcState* states, int in
     for (int o = 16; o > 0; o >>= 1) {
         dmax = fmaxf(dmax, __shfl_xor_sync(0xffffffffu, dmax, o));
         zmax = fmaxf(zmax, __shfl_xor_sync(0xffffffffu, zmax, o));
+        tmax = fmaxf(tmax, __shfl_xor_sync(0xffffffffu, tmax, o));
     }
-    if ((tid & 31) == 0) { s_red[0][tid >> 5] = dmax; s_red[1][tid >> 5] = zmax; }
+    if ((tid & 31) == 0) { s_red[0][tid >> 5] = dmax; s_red[1][tid >> 5] = zmax; s_red[2][tid >> 5] = tmax; }
     __syncthreads();
     // merge of the two sorted lists (stable: first child first on ties)
     for (int i = tid; i < nm; i += blockDim.x) {
@@ -218,9 +225,9 @@ dc_prep_kernel(const DcMat* mats, const DcMerge* merges, DcState* states, int in
     }
     __syncthreads();
     if (tid != 0) return;
-    dmax = 0.f; zmax = 0.f;
-    for (int i = 0; i < 32; ++i) { dmax = fmaxf(dmax, s_red[0][i]); zmax = fmaxf(zmax, s_red[1][i]); }
-    const float tol = 8.f * FEPS * fmaxf(dmax, zmax);
+    dmax = 0.f; zmax = 0.f; tmax = 0.f;
+    for (int i = 0; i < 32; ++i) { dmax = fmaxf(dmax, s_red[0][i]); zmax = fmaxf(zmax, s_red[1][i]); tmax = fmaxf(tmax, s_red[2][i]); }
+    const float tol = 8.f * FEPS * fmaxf(dmax, tmax * zmax);
     float* dl = mt.dl + off;
     float* w = mt.w + off;
     int* rotab = mt.rotab + 2 * off;

@@ -222,10 +222,19 @@ __global__ void syrk_reduce_ema_kernel(const float* __restrict__ partial, int ks
     const bool upper = (i / TILE < j / TILE) || (i / TILE == j / TILE && i <= j);
     const int r = upper ? i : j;
     const int c = upper ? j : i;
-    float s = 0.f;
-    for (int z = 0; z < ksplit; ++z) s += partial[(long)z * n * n + (long)r * n + c];
+    // up to ~800 partials (conv1: 401 408 rows in chunks of 512): summed in double -- a sequential fp32 sum loses
+    // ~sqrt(ksplit) ulp, which the conditioning of the preconditioner amplifies (the kernel is memory bound anyway)
+    double s = 0.0;
+    const float* p = partial + (long)r * n + c;
+    const long stride = (long)n * n;
+    int z = 0;
+    for (; z + 4 <= ksplit; z += 4) {                              // 4 loads in flight
+        const float a0 = p[(long)z * stride], a1 = p[(long)(z + 1) * stride], a2 = p[(long)(z + 2) * stride], a3 = p[(long)(z + 3) * stride];
+        s += ((double)a0 + (double)a1) + ((double)a2 + (double)a3);
+    }
+    for (; z < ksplit; ++z) s += (double)p[(long)z * stride];
     const float old = first_step ? (i == j ? 1.f : 0.f) : factor[idx];
-    factor[idx] = fmaf(alpha, scale * s, (1.f - alpha) * old);
+    factor[idx] = fmaf(alpha, scale * (float)s, (1.f - alpha) * old);
 }
 
 // mean over the sequence axis: in (B, T, D) -> out (B, D)   (kfac/utils.py:98-99,133-134)
@@ -297,12 +306,12 @@ static int run_syrk(const L& ld, int n, long K, float scale, float alpha, int fi
     const int ksplit = (int)((K + kchunk - 1) / kchunk);
     const int T = cdiv(n, TILE);
     dim3 grid(T * (T + 1) / 2, ksplit);
-    if (use_tc_gemm() && K >= 64) {
-        static bool attr_done = false;           // per loader instantiation
-        if (!attr_done) {
-            KFACB_CHECK_CUDA(cudaFuncSetAttribute(tc_syrk_ema_kernel<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, tcg::SMEM));
-            attr_done = true;
-        }
+    // the tensor-core path bounds its in-TMEM accumulation chain by the k-chunk (round-toward-zero accumulation, tc_gemm.cuh);
+    // if the workspace / split caps of choose_ksplit push the chunk beyond twice that bound (batches of millions of rows),
+    // the exact-fp32 SIMT kernel takes over instead of silently accumulating a biased chain
+    if (use_tc_gemm() && K >= 64 && kchunk <= 2 * TC_MAX_KCHUNK) {
+        // (set per call: the attribute is per device, and one process may drive several GPUs)
+        KFACB_CHECK_CUDA(cudaFuncSetAttribute(tc_syrk_ema_kernel<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, tcg::SMEM));
         tc_syrk_ema_kernel<L><<<grid, tcg::THREADS, tcg::SMEM, st>>>(ld, n, (int)K, kchunk, scale, alpha,
                                                                    first_step, factor, partial);
     } else {

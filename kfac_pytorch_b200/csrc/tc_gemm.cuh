@@ -319,11 +319,9 @@ tc_gemm_kernel(LA la, LB lb, Epi epi, int M, int N, int K) {
 
 template <class LA, class LB, class Epi, bool FLUSH>
 static inline cudaError_t launch_variant(const LA& la, const LB& lb, const Epi& epi, int M, int N, int K, cudaStream_t st) {
-    static bool attr_done = false;       // per template instantiation
-    if (!attr_done) {
+    {   // per call: the attribute is per device, and one process may drive several GPUs
         cudaError_t e = cudaFuncSetAttribute(tc_gemm_kernel<LA, LB, Epi, FLUSH>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
         if (e != cudaSuccess) return e;
-        attr_done = true;
     }
     dim3 grid(cdiv(N, TILE), cdiv(M, TILE));
     tc_gemm_kernel<LA, LB, Epi, FLUSH><<<grid, THREADS, SMEM, st>>>(la, lb, epi, M, N, K);

@@ -135,7 +135,7 @@ def secular_roots(dl, w2, rho):
     return lam, delta
 
 
-def dc_merge(d1, Z1, d2, Z2, e_split):
+def dc_merge(d1, Z1, d2, Z2, e_split, tnorm=1.0):
     """Children (d sorted ascending, Zt rows = eigenvectors) -> merged (d, Zt)."""
     n1, n2 = len(d1), len(d2)
     nm = n1 + n2
@@ -148,7 +148,10 @@ def dc_merge(d1, Z1, d2, Z2, e_split):
     z = np.concatenate([Z1[:, n1 - 1], sgn * Z2[:, 0]]).astype(f32) * inv_sqrt2
     dd = np.concatenate([d1, d2]).astype(f32)
     order = np.argsort(dd, kind='stable')
-    tol = f32(8) * EPS * max(np.max(np.abs(dd)), np.max(np.abs(z)))
+    # LAPACK (slaed2) uses 8 eps max(|d|max, |z|max) on a matrix SCALED to unit max-norm (sstedc); unscaled, the
+    # dimensionless z has to carry the scale of the tridiagonal matrix, otherwise factors of small norm (K-FAC's
+    # conv A factors are ~0.0025 I + ..) deflate far too eagerly (measured: 6e-5 instead of 3e-6)
+    tol = f32(8) * EPS * max(np.max(np.abs(dd)), f32(tnorm) * np.max(np.abs(z)))
     # ---- deflation scan (sequential) ----
     nd_idx, defl = [], []          # rows of Zin
     rot = []
@@ -216,6 +219,7 @@ def dc_model(d, e, leaf=32):
     n = len(d)
     b = leaf_bounds(n, leaf)
     dm = np.array(d, dtype=f32)
+    tnorm = max(np.max(np.abs(d)), np.max(np.abs(e)) if len(e) else 0.0)       # max-norm of the tridiagonal matrix
     for k in b[1:-1]:                 # rank-one tear at every leaf boundary
         dm[k - 1] -= abs(e[k - 1])
         dm[k] -= abs(e[k - 1])
@@ -230,7 +234,7 @@ def dc_model(d, e, leaf=32):
         for i in range(0, len(nodes) - 1, 2):
             a, m, d1, Z1 = nodes[i]
             _, c, d2, Z2 = nodes[i + 1]
-            dn, Zn, K = dc_merge(d1, Z1, d2, Z2, e[m - 1])
+            dn, Zn, K = dc_merge(d1, Z1, d2, Z2, e[m - 1], tnorm)
             ks.append((c - a, K))
             nxt.append((a, c, dn, Zn))
         if len(nodes) % 2:
