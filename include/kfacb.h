@@ -121,7 +121,8 @@ int    kfacb_factor_update(const kfacb_layer_t* layers, int32_t count,
  *             kernel (teams of CTAs per matrix), divide and conquer on the
  *             tridiagonal matrices, block-reflector back-transformation on the
  *             tensor cores.  Fixed launch sequence: the call only ENQUEUES work (no
- *             convergence test, no host synchronisation, CUDA-graph capturable).
+ *             convergence test, no host synchronisation).  Not graph-capturable as is: the per-call
+ *             job tables are uploaded from a transient host image.
  *             n <= 8192.  (KFACB_EIGH_ALGO=jacobi selects the round-1 block-Jacobi
  *             path, which does synchronise the host on its progress events.)
  * sweeps_out (device int32[count], may be NULL) receives the number of Jacobi

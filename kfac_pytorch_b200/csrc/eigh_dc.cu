@@ -5,7 +5,7 @@
 //   (3) Q = Q_H Z                block-reflector back-transformation on the tensor cores (tcgen05 3xTF32)
 //   (4) floor + write             d <- lam * (lam > eps), Q column-wise (kfac/utils.py:22-25, eigen_dp.py:62-75)
 // Replaces the round-1 block-Jacobi path as the default: ~10x fewer flops, a FIXED launch sequence (no convergence
-// test, no host synchronisation: the call only enqueues work and is CUDA-graph capturable) and LAPACK-class
+// test, no host synchronisation: the call only enqueues work) and LAPACK-class
 // accuracy (reconstruction ~1e-6).  tools/eigh_trd_dc_model.py is the same algorithm in numpy.
 //
 // D&C, per merge of two solved children (d1, Z1), (d2, Z2) torn apart at sub-diagonal element e (rho = 2|e|,
