@@ -39,36 +39,43 @@ __global__ void pi_damp_kernel(const DampJob* jobs, float sqrt_damping) {
     for (int i = threadIdx.x; i < jb.nG; i += blockDim.x) jb.G[(long)i * jb.nG + i] += dg;
 }
 
-// D = inverse of the nb x nb diagonal block at (k0, k0) of W (n x n).  one CTA, 256 threads
-__global__ void __launch_bounds__(256)
+// D = inverse of the nb x nb diagonal block at (k0, k0) of W (n x n).  one CTA, 1024 threads: thread (i, jq) owns the
+// 4 elements a[i][4 jq .. 4 jq + 3] in REGISTERS for the whole elimination; a pivot step publishes row s and column s
+// through shared memory (one barrier per pivot).  This kernel is the serial link of every block step.
+constexpr int GJ_DIAG_THREADS = GJ_NB * GJ_NB / 4;
+__global__ void __launch_bounds__(GJ_DIAG_THREADS)
 gj_diag_kernel(const float* __restrict__ W, int n, int k0, int nb, float* __restrict__ D) {
-    __shared__ float a[GJ_NB][GJ_NB + 1];
-    __shared__ float colv[GJ_NB], rowv[GJ_NB];
-    const int tid = threadIdx.x;
-    for (int e = tid; e < GJ_NB * GJ_NB; e += 256) {
-        const int i = e / GJ_NB, j = e - i * GJ_NB;
-        a[i][j] = (i < nb && j < nb) ? W[(long)(k0 + i) * n + k0 + j] : (i == j ? 1.f : 0.f);
+    __shared__ float rowv[2][GJ_NB], colv[2][GJ_NB];
+    const int tid = threadIdx.x, i = tid >> 4, j0 = (tid & 15) * 4;
+    float a[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+        const int j = j0 + u;
+        a[u] = (i < nb && j < nb) ? W[(long)(k0 + i) * n + k0 + j] : (i == j ? 1.f : 0.f);
     }
-    __syncthreads();
     for (int s = 0; s < nb; ++s) {
-        const float piv = 1.f / a[s][s];
-        if (tid < GJ_NB) { colv[tid] = a[tid][s]; rowv[tid] = a[s][tid]; }
+        const int b = s & 1;                                   // double-buffered: one barrier per pivot
+        if (i == s) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) rowv[b][j0 + u] = a[u];
+        }
+        if ((s >> 2) == (tid & 15)) colv[b][i] = a[s & 3];
         __syncthreads();
-        for (int e = tid; e < GJ_NB * GJ_NB; e += 256) {
-            const int i = e / GJ_NB, j = e - i * GJ_NB;
+        const float piv = 1.f / rowv[b][s];
+        const float ci = colv[b][i] * piv;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int j = j0 + u;
             float v;
             if (i == s && j == s) v = piv;
-            else if (i == s) v = rowv[j] * piv;
-            else if (j == s) v = -colv[i] * piv;
-            else v = a[i][j] - colv[i] * piv * rowv[j];
-            a[i][j] = v;
+            else if (i == s) v = a[u] * piv;
+            else if (j == s) v = -ci;
+            else v = fmaf(-ci, rowv[b][j], a[u]);
+            a[u] = v;
         }
-        __syncthreads();
     }
-    for (int e = tid; e < GJ_NB * GJ_NB; e += 256) {
-        const int i = e / GJ_NB, j = e - i * GJ_NB;
-        D[e] = a[i][j];
-    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) D[i * GJ_NB + j0 + u] = a[u];
 }
 
 // whole-matrix path for n <= 64: out = M^-1 directly.  one CTA per matrix
@@ -146,18 +153,27 @@ struct EpiRankUpdate {
         if ((unsigned)(m - k0) < (unsigned)nb || (unsigned)(c - k0) < (unsigned)nb) return;
         W[(long)m * n + c] += v;
     }
+    // read-modify-write form for the tensor-core kernel (loads batched ahead of the stores, tc_gemm.cuh)
+    __device__ __forceinline__ float* addr(int m, int c) const {
+        if ((unsigned)(m - k0) < (unsigned)nb || (unsigned)(c - k0) < (unsigned)nb) return nullptr;
+        return W + (long)m * n + c;
+    }
+    __device__ __forceinline__ float combine(float old, float v) const { return old + v; }
 };
 
 // W[k rows][j] = D W[k rows][j] (j outside k);  W[i][k cols] = C[i] (i outside k);  W_kk = D
-__global__ void gj_fix_kernel(float* __restrict__ W, int n, int k0, int nb,
-                              const float* __restrict__ D, const float* __restrict__ C) {
+// Two jobs per CTA of 128 threads: (1) the thread of column j updates W[k0 .. k0+nb)[j] (coalesced along j; D is read
+// through registers 4 at a time, the 64 old values stay in registers); (2) the same 128 rows get their column block
+// from C with lanes walking the 64 contiguous columns of a row (coalesced 256-byte row pieces; thread-per-row copies
+// touched 64 separate sectors per instruction and were the slowest kernel of the inverse).
+__global__ void __launch_bounds__(128)
+gj_fix_kernel(float* __restrict__ W, int n, int k0, int nb,
+              const float* __restrict__ D, const float* __restrict__ C) {
     __shared__ float ds[GJ_NB][GJ_NB + 1];
     for (int e = threadIdx.x; e < GJ_NB * GJ_NB; e += blockDim.x) ds[e / GJ_NB][e % GJ_NB] = D[e];
     __syncthreads();
-    const int j = blockIdx.x * blockDim.x + threadIdx.x;     // column (row-block fix) / row (col-block fix)
-    if (j >= n) return;
-    const bool inside = (unsigned)(j - k0) < (unsigned)nb;
-    if (!inside) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;     // column of the row-block fix
+    if (j < n && (unsigned)(j - k0) >= (unsigned)nb) {
         float old[GJ_NB];
 #pragma unroll 8
         for (int s = 0; s < GJ_NB; ++s) old[s] = s < nb ? W[(long)(k0 + s) * n + j] : 0.f;
@@ -167,10 +183,15 @@ __global__ void gj_fix_kernel(float* __restrict__ W, int n, int k0, int nb,
             for (int s = 0; s < GJ_NB; ++s) acc = fmaf(ds[r][s], old[s], acc);
             W[(long)(k0 + r) * n + j] = acc;
         }
-        for (int c = 0; c < nb; ++c) W[(long)j * n + k0 + c] = C[(long)j * GJ_NB + c];
-    } else {
-        const int r = j - k0;
-        for (int c = 0; c < nb; ++c) W[(long)j * n + k0 + c] = ds[r][c];
+    }
+    // column block (and the diagonal block itself) of the rows of this CTA: warp w takes rows w, w + 4, ..
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int rr = warp; rr < (int)blockDim.x; rr += 4) {
+        const int i = blockIdx.x * blockDim.x + rr;
+        if (i >= n) break;
+        const bool inside = (unsigned)(i - k0) < (unsigned)nb;
+        for (int c = lane; c < nb; c += 32)
+            W[(long)i * n + k0 + c] = inside ? ds[i - k0][c] : C[(long)i * GJ_NB + c];
     }
 }
 
@@ -196,7 +217,7 @@ static int invert_large(const float* M, float* out, int n, float* D, float* C, c
     KFACB_CHECK_CUDA(cudaMemcpyAsync(out, M, (size_t)n * n * sizeof(float), cudaMemcpyDeviceToDevice, st));
     for (int k0 = 0; k0 < n; k0 += GJ_NB) {
         const int nb = (n - k0 < GJ_NB) ? n - k0 : GJ_NB;
-        gj_diag_kernel<<<1, 256, 0, st>>>(out, n, k0, nb, D);
+        gj_diag_kernel<<<1, GJ_DIAG_THREADS, 0, st>>>(out, n, k0, nb, D);
         KFACB_CHECK_LAUNCH();
         KFACB_CHECK_CUDA(launch_gemm_auto(LdPanel{out, n, k0, nb}, LdDcol{D, nb}, EpiNegStore{C}, n, nb, nb, st));
         KFACB_CHECK_CUDA(launch_gemm_auto(LdC{C, n, nb}, LdRowBlk{out, n, k0, nb},
