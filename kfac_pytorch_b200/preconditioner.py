@@ -152,6 +152,9 @@ class KFAC(optim.Optimizer):
         # half the gradient bytes on the wire of all-reduce + exchange.  The KL-clip sum is formed from the owners'
         # partials with one 8-byte all-reduce (keyword-only; DP variants; not part of the reference signature)
         self.fuse_grad_reduce = bool(fuse_grad_reduce)
+        if (self.overlap_factor_capture or self.fuse_grad_reduce) and not self.is_dp:
+            raise ValueError('overlap_factor_capture / fuse_grad_reduce are implemented for the distributed-preconditioning '
+                             'variants (eigen_dp, inverse_dp) only, not for %r' % self.variant)
         self._gslab = None
         self._vg = None
         self._cap_stream = None

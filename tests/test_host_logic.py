@@ -300,3 +300,14 @@ def test_fused_gradient_reduce_matches_allreduce_then_step(variant):
             assert np.allclose(a, b, rtol=2e-4, atol=1e-7), np.abs(a - b).max()     # fp32: gloo sums in another order
     for a, b in zip(out[0][True], out[1][True]):
         assert np.array_equal(a, b)         # every rank ends with identical gradients
+
+
+def test_optional_flags_are_refused_for_the_mpd_variants():
+    import kfac_pytorch_b200 as kfac
+    from tests.oracle_engine import OracleEngine
+    _fresh_backend()
+    model = torch.nn.Linear(4, 3)
+    for flag in ('overlap_factor_capture', 'fuse_grad_reduce'):
+        with pytest.raises(ValueError, match='distributed-preconditioning'):
+            kfac.get_kfac_module('eigen')(model, engine=OracleEngine(), **{flag: True})
+    kfac.get_kfac_module('eigen_dp')(model, engine=OracleEngine(), overlap_factor_capture=True, fuse_grad_reduce=True)
