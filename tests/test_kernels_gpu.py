@@ -234,6 +234,50 @@ def test_precondition_and_finalize(eng, dims):
     assert nu.item() == 1.0 and _rel(wd2, vw) < 1e-6
 
 
+@pytest.mark.parametrize('bias', [True, False])
+def test_pack_grads_and_split_finalize(eng, bias):
+    """kfacb_pack_grads / kfacb_finalize_dot / kfacb_finalize_write (the pieces of the fused gradient-reduce path): two
+    layers; the split form with the dot summed over 'owners' equals kfacb_finalize_grads on the same data."""
+    from kfac_pytorch_b200.native import LayerDesc, KFACB_LINEAR
+    gen = torch.Generator().manual_seed(7)
+    descs, vs, ws, bs = [], [], [], []
+    for (dA, dG) in ((33, 20), (130, 9)):
+        d = LayerDesc(); d.kind = KFACB_LINEAR; d.has_bias = int(bias); d.batch = 1; d.seq = 1
+        d.in_c = dA - int(bias); d.out_c = dG; d.kh = d.kw = d.sh = d.sw = 1
+        descs.append(d)
+        vs.append(torch.randn(dG, dA, generator=gen).to(DEV))
+        ws.append(torch.randn(dG, dA - int(bias), generator=gen).to(DEV))
+        bs.append(torch.randn(dG, generator=gen).to(DEV) if bias else None)
+    # pack: [W | b] per layer, contiguous
+    dst = [torch.full((d.dA * d.dG,), float('nan'), device=DEV) for d in descs]
+    eng.pack_grads(descs, ws, bs, dst)
+    for d, w, b, o in zip(descs, ws, bs, dst):
+        nw = w.numel()
+        assert torch.equal(o[:nw], w.reshape(-1))
+        if bias:
+            assert torch.equal(o[nw:], b)
+    # dot of each 'owner' (one layer each) from the PACKED gradients, summed like the 8-byte all-reduce would
+    tot = torch.zeros(1, dtype=torch.float64, device=DEV)
+    part = torch.zeros(1, dtype=torch.float64, device=DEV)
+    for d, v, o, w in zip(descs, vs, dst, ws):
+        nw = w.numel()
+        eng.finalize_dot([d], [v], [o[:nw]], [o[nw:] if bias else None], part)
+        tot += part
+    ref = sum(float((v.double() * (torch.cat([w, b[:, None]], 1) if bias else w).double()).sum()) for v, w, b in zip(vs, ws, bs))
+    assert abs(tot.item() - ref) <= 1e-6 * abs(ref) + 1e-9            # (the products are formed in fp32 like the reference, the sum in double)
+    # write from the global sum == the monolithic call
+    nu1, nu2 = torch.zeros(1, device=DEV), torch.zeros(1, device=DEV)
+    w1 = [w.clone() for w in ws]; b1 = [None if b is None else b.clone() for b in bs]
+    w2 = [w.clone() for w in ws]; b2 = [None if b is None else b.clone() for b in bs]
+    eng.finalize(descs, vs, w1, b1, 0.1, 0.001, False, nu1)
+    eng.finalize_write(descs, vs, w2, b2, tot, 0.1, 0.001, False, nu2)
+    assert abs(nu1.item() - nu2.item()) <= 1e-6 * nu1.item() and nu1.item() < 1.0
+    for a, c in zip(w1 + [x for x in b1 if x is not None], w2 + [x for x in b2 if x is not None]):
+        assert torch.allclose(a, c, rtol=1e-6, atol=0)
+    eng.finalize_write(descs, vs, w2, b2, None, 0.1, None, True, nu2)        # clip off: nu = 1, no sum needed
+    assert nu2.item() == 1.0 and torch.equal(w2[0], vs[0][:, :w2[0].shape[1]].contiguous())
+
+
 def test_bad_arguments_return_status_not_abort(eng):
     from kfac_pytorch_b200.native import KfacbError, LayerDesc
     d = LayerDesc(); d.kind = 7; d.batch = 1; d.in_c = 2; d.out_c = 2
