@@ -1,3 +1,3 @@
 mkdir -p gpurun_out
 rm -f gpurun_out/r3s_*
-bash tools/run_multi.sh 8 r3s "r50_rr:" "r50_greedy:--partition greedy"
+bash tools/run_multi.sh 8 r3s "r50_rr:"
