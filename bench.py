@@ -453,8 +453,8 @@ def run_ours(args):
                     name='trd::trd_kernel (persistent team-scheduled Householder tridiagonalisation; dominant kernel)',
                     bound='hbm', ms=prof['ms_trd'], share_of_step=prof['ms_trd'] / ms_per_step,
                     algorithmic_bytes=prof['bytes_trd'], achieved=gbs, peak=peaks['hbm'], unit='GB/s', frac=gbs / peaks['hbm'],
-                    note='algorithmic bytes = sum (2/3 + 1/12) n^3: the lower triangle of the trailing matrix read once per reduced column '
-                         '(symmetric product, TMA-fed) + one read-modify-write of the trailing matrix per 32-column panel; launches per step: 1',
+                    note='algorithmic bytes = sum (2/3 + 1/24) n^3: the lower triangle of the trailing matrix read once per reduced column '
+                         '(symmetric product, TMA-fed) + one read-modify-write of that triangle per 32-column panel; launches per step: 1',
                     other_stages_ms=dict(divide_and_conquer=prof['ms_dc'], backtransform_and_write=prof['ms_bt']),
                     ctas=int(prof['grid']), matrices=int(prof['matrices']))
     phase_report = {}

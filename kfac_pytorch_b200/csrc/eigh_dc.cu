@@ -953,7 +953,7 @@ int eigh_tdc_last_profile(double* out8) {
     if (cudaEventElapsedTime(&t, s->ev[0], s->ev[1]) == cudaSuccess) out8[0] = t;      // tridiagonalisation (copy + persistent kernel)
     if (cudaEventElapsedTime(&t, s->ev[1], s->ev[2]) == cudaSuccess) out8[1] = t;      // divide and conquer
     if (cudaEventElapsedTime(&t, s->ev[2], s->ev[3]) == cudaSuccess) out8[2] = t;      // back-transformation + write
-    out8[3] = s->bytes_trd;     // algorithmic bytes of the tridiagonalisation: sum (2/3 + 1/12) n^3 -- the lower triangle of the trailing
+    out8[3] = s->bytes_trd;     // algorithmic bytes of the tridiagonalisation: sum (2/3 + 1/24) n^3 -- the lower triangle of the trailing
                                 // matrix read once per column (symmetric product) + one read-modify-write of it per 32-column panel
     out8[4] = s->n3;            // sum n^3 of the blocked matrices
     out8[5] = s->nb; out8[6] = s->grid;
@@ -1072,7 +1072,7 @@ int eigh_tdc_run(const int32_t* n, const int* idx, int nb, const float* const* M
     StageEvents* sev = stage_events();
     if (sev) {
         sev->nb = nb; sev->grid = pl.grid; sev->bytes_trd = 0; sev->n3 = 0;
-        for (int a = 0; a < nb; ++a) { const double n3 = (double)pl.ml[a].n * pl.ml[a].n * pl.ml[a].n; sev->n3 += n3; sev->bytes_trd += 0.75 * n3; }
+        for (int a = 0; a < nb; ++a) { const double n3 = (double)pl.ml[a].n * pl.ml[a].n * pl.ml[a].n; sev->n3 += n3; sev->bytes_trd += (2.0 / 3.0 + 1.0 / 24.0) * n3; }
         cudaEventRecord(sev->ev[0], st);
     }
     // ---- (1) tridiagonalisation ----
