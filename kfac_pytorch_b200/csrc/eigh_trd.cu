@@ -1,23 +1,27 @@
 // eigh_trd.cu -- Householder tridiagonalisation A = Q_H T Q_H^T of a BATCH of symmetric fp32 matrices in ONE
-// persistent kernel (first stage of the n > 128 path of kfacb_eigh_batched; replaces the LAPACK ssytrd inside
+// persistent kernel (first stage of the n > 64 path of kfacb_eigh_batched; replaces the LAPACK ssytrd inside
 // torch.linalg.eigh of the reference, kfac/utils.py:22-25 / kfac_preconditioner_eigen_dp.py:62-75).
 //
 // Why this shape on B200.  The reduction is a chain of n dependent columns; each column needs one symmetric
-// matrix-vector product with the trailing matrix (BLAS-2: 4 m^2 bytes at column j, m = n - j) -- HBM/L2
-// bandwidth and LATENCY bound, nothing for the tensor cores.  So:
-//   * the batch is scheduled on the 148 SMs as TEAMS of CTAs (1 CTA / SM, cooperative launch): a big factor gets a
-//     team sized by a latency + bandwidth cost model, small factors are packed several to a single-CTA team;
-//     all matrices advance concurrently and HBM stays saturated while each chain only pays its own latency;
-//   * inside a team, rows are dealt cyclically (row i -> CTA i mod team), a warp does a whole row of the product
-//     (coalesced float4 ld.global.cg, the reflector in shared memory), and a column costs exactly TWO team
-//     barriers (a release/acquire counter in L2, ~1 us): column+norm | barrier | reflector+product+panel inner
-//     products | barrier.  Everything else that LAPACK's slatrd does with extra synchronisation (w = p - ..v,
-//     the panel corrections V(W^T v) + W(V^T v), v^T p) is algebraically folded so that it needs only the sums
-//     made in the same pass; partial sums go through per-CTA slots and are added in a fixed order
-//     (deterministic, no float atomics);
+// matrix-vector product with the trailing matrix (BLAS-2: 2 m^2 bytes of its lower triangle at column j,
+// m = n - j) -- HBM/L2 bandwidth and LATENCY bound, nothing for the tensor cores.  So:
+//   * the batch is scheduled on the SMs as TEAMS of CTAs (1 CTA / SM, cooperative launch): a big factor gets a
+//     team sized by a cost model fitted to measurements (job_time below), small factors are packed several to a
+//     single-CTA team; all matrices advance concurrently and each chain only pays its own latency;
+//   * inside a team, rows are dealt in 8-row blocks (block b -> CTA b mod team).  The symmetric product reads the
+//     LOWER triangle only: a work unit is (owned 8-row block, 128-column chunk) = one 4 KB box that a warp fetches
+//     with ONE TMA request (cp.async.bulk.tensor.2d through the tensor map of the work array) into its private
+//     2-slot shared-memory ring, completion on an mbarrier; the warp then forms the 8 row sums (9 shuffles) and the
+//     128 transposed sums of the box; units are numbered chunk-major and dealt to the 16 warps in equal ranges;
+//   * a column costs exactly TWO team barriers (release / acquire on a counter in L2): column + |x|^2 + the raw
+//     panel inner products | barrier | reflector + product | barrier.  Everything else that LAPACK's slatrd does
+//     with extra synchronisation (w = p - ..v, the panel corrections V(W^T v) + W(V^T v), v^T p) is folded
+//     algebraically so that it needs only the sums made in the same pass; the team-wide partial sums go through
+//     per-CTA slots in global memory and are added in a fixed order (no float atomics in global memory; inside a
+//     CTA the product accumulates with shared-memory float atomics: runs agree to rounding, not bitwise);
 //   * updates are delayed LAPACK-style: within a panel of 32 columns the trailing matrix is read only, the
-//     rank-64 update A -= V W^T + W V^T runs once per panel as an exact-fp32 register-tiled SIMT GEMM on 128x128
-//     tiles (K = 64: too skinny to be worth a TMEM round trip; 4/3 n^3 flops in total, < 10 % of the step);
+//     rank-64 update A -= V W^T + W V^T runs once per panel on the lower triangle of 128x128 tiles as an
+//     exact-fp32 register-tiled SIMT GEMM (K = 64: too skinny to be worth a TMEM round trip; 2/3 n^3 flops);
 //   * reflector j is left in the dead row j of the work array (T[j][j+1..n)), K-contiguous, which is exactly the
 //     operand layout the tensor-core back-transformation (eigh_dc.cu) wants.
 // The formulas are pinned by tools/eigh_trd_dc_model.py (same phases in numpy).
