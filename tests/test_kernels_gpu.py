@@ -288,6 +288,25 @@ def test_bad_arguments_return_status_not_abort(eng):
         eng.eigh([torch.zeros(2, 2)], [t], [t[0]], 1e-10)
 
 
+@pytest.mark.parametrize('scale', [1.0, 2.5e-3], ids=str)
+def test_eigh_accuracy_does_not_depend_on_the_matrix_norm(eng, scale):
+    """K-FAC's conv A factors are ~0.0025 I + small (kfac/utils.py:85-96 divides by the spatial size twice).  The divide
+    and conquer's deflation tolerance must carry the norm of the tridiagonal matrix (LAPACK scales to unit norm first);
+    an absolute tolerance reconstructed ResNet-50's conv1 factor to 6.9e-5 only (profiles/r02_eigh_accuracy.txt).
+    CPU twin: tests/test_eigh_model.py."""
+    gen = torch.Generator(device=DEV).manual_seed(3)
+    for n in (147, 576):
+        x = torch.randn(400 * n, n, device=DEV, generator=gen)
+        A = (scale * (0.05 * torch.eye(n, device=DEV) + 0.95 * (x.t() @ x) / x.shape[0])).contiguous()
+        Q = torch.empty_like(A); d = torch.empty(n, device=DEV)
+        eng.eigh([A], [Q], [d], 1e-10)
+        Ad, Qd, dd = A.double(), Q.double(), d.double()
+        rec = (((Qd * dd) @ Qd.t() - Ad).norm() / Ad.norm()).item()
+        ref = torch.linalg.eigvalsh(Ad)
+        assert rec < 2e-5, (scale, n, rec)
+        assert (dd - ref).abs().max().item() <= 1e-5 * ref.abs().max().item(), (scale, n)
+
+
 @pytest.mark.parametrize('ns', [(2304,), (4608, 512), (1664, 1664)], ids=str)
 def test_eigh_back_to_back_without_host_sync(eng, ns):
     """Pipelined use (consecutive step() calls, no host synchronisation in between -- what bench.py and real
